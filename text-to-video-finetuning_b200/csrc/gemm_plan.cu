@@ -1,0 +1,351 @@
+// Host-side planners: turn convolution / batched-GEMM problems into coefficient tables for the affine TMA GEMM
+// (gemm_tc.cuh) and export them through the C ABI declared in include/t2v_b200.h.
+#include "common.h"
+#include "gemm_tc.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+using namespace t2v;
+
+namespace {
+
+struct Box3 {
+    int w, h, n;
+};
+
+// Factor `prod` (a power of two) into (w,h,n) box extents over a (W,H,N) pixel space, maximising useful coverage.
+Box3 choose_pixel_box(int prod, int W, int H, int N) {
+    Box3 best{prod, 1, 1};
+    double best_eff = -1.0;
+    for (int bw = prod; bw >= 1; bw >>= 1) {
+        for (int bh = prod / bw; bh >= 1; bh >>= 1) {
+            const int bn = prod / (bw * bh);
+            if (bw > 256 || bh > 256 || bn > 256) continue;
+            const double cover = double((W + bw - 1) / bw) * bw * double((H + bh - 1) / bh) * bh * double((N + bn - 1) / bn) * bn;
+            const double eff = double(W) * H * N / cover;
+            if (eff > best_eff + 1e-9) {
+                best_eff = eff;
+                best = Box3{bw, bh, bn};
+            }
+        }
+    }
+    return best;
+}
+
+// UMMA N for a problem with `row_tiles` row tiles and `ncols` columns: fewest waves, then least padding.
+int choose_block_n(int64_t row_tiles, int ncols, bool mn_major_b) {
+    const int sms = device_sm_count();
+    int best = 16;
+    double best_cost = 1e30;
+    for (int bn = 256; bn >= 16; bn -= 16) {
+        if (bn > 16 && bn - 16 >= ncols) continue;  // strictly more padding than needed
+        const int64_t col_tiles = (ncols + bn - 1) / bn;
+        const int64_t tiles = row_tiles * col_tiles;
+        const int64_t waves = (tiles + sms - 1) / sms;
+        // per-tile time ~ max(MMA time ~ bn, A-operand smem fill floor)
+        double cost = double(waves) * std::max(bn, 96);
+        if (mn_major_b) cost *= 1.0 + 0.02 * ((64 - bn % 64) % 64) / 64.0;  // unused part of the last 64-wide box
+        if (cost < best_cost - 1e-9) {
+            best_cost = cost;
+            best = bn;
+        }
+    }
+    return best;
+}
+
+void finish_common(GemmParams& p, bool b_mn) {
+    p.stage_bytes_a = kBlockM * 128;
+    p.stage_bytes_b = b_mn ? ((p.block_n + 63) / 64) * 8192 : p.block_n * 128;
+    const int budget = 232448 - 1024 - 256;
+    p.num_stages = std::min<int>(kMaxStages, budget / (p.stage_bytes_a + p.stage_bytes_b));
+    int64_t tiles = 1;
+    for (int i = 0; i < 6; ++i) tiles *= p.tdim[i];
+    p.num_tiles = static_cast<int32_t>(tiles);
+    p.kb_total = p.kdim[0] * p.kdim[1] * p.kdim[2];
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+void fill_epilogue(GemmParams& p, const T2VEpilogue* e, void* out, int out_mode_default) {
+    p.out = out;
+    p.alpha = e ? e->alpha : 1.0f;
+    p.bias = e ? e->bias : nullptr;
+    p.rowbias = e ? e->rowbias : nullptr;
+    p.residual = e ? e->residual : nullptr;
+    p.out_mode = e ? (e->out_fp32 ? OUT_F32 : OUT_BF16) : out_mode_default;
+    p.flags = 0;
+    if (p.bias) p.flags |= EPI_BIAS;
+    if (p.rowbias) p.flags |= EPI_ROWBIAS;
+    if (p.residual) p.flags |= EPI_RESIDUAL;
+}
+
+void set_vec_flag(GemmParams& p) {
+    bool ok = aligned16(p.out) && (!p.residual || aligned16(p.residual)) && (!p.bias || aligned16(p.bias)) &&
+              (!p.rowbias || aligned16(p.rowbias));
+    const int64_t strides[] = {p.ldw, p.ldh, p.ldn, p.otc[0], p.otc[1], p.otc[2], p.otc[3], p.otc[4], p.otc[5], p.rb_ld};
+    for (int64_t s : strides) ok = ok && (s % 8 == 0);
+    if (ok) p.flags |= EPI_VEC;
+}
+
+int check_channels(int c, const char* what) {
+    if (c <= 0 || c % 8 != 0) return fail(-2, "%s=%d must be a positive multiple of 8 (16-byte TMA rows)", what, c);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int t2v_conv_fwd(const void* x, const void* w, void* y, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                 int32_t KH, int32_t KW, int32_t stride, int32_t pad_h0, int32_t pad_h1, int32_t pad_w0, int32_t pad_w1,
+                 const T2VEpilogue* epi, void* stream) {
+    if (int r = check_channels(Cin, "Cin")) return r;
+    if (Cout <= 0 || N <= 0 || H <= 0 || W <= 0) return fail(-2, "conv_fwd: bad shape");
+    if (stride != 1 && stride != 2) return fail(-2, "conv_fwd: stride %d unsupported", stride);
+    const int Ho = (H + pad_h0 + pad_h1 - KH) / stride + 1, Wo = (W + pad_w0 + pad_w1 - KW) / stride + 1;
+    if (Ho <= 0 || Wo <= 0) return fail(-2, "conv_fwd: empty output");
+    GemmParams p;
+    std::memset(&p, 0, sizeof(p));
+    const Box3 bx = choose_pixel_box(kBlockM, Wo, Ho, N);
+    const int64_t row_tiles = int64_t((Wo + bx.w - 1) / bx.w) * ((Ho + bx.h - 1) / bx.h) * ((N + bx.n - 1) / bx.n);
+    p.block_n = choose_block_n(row_tiles, Cout, false);
+    p.tdim[0] = (Cout + p.block_n - 1) / p.block_n;
+    p.tdim[1] = (Wo + bx.w - 1) / bx.w;
+    p.tdim[2] = (Ho + bx.h - 1) / bx.h;
+    p.tdim[3] = (N + bx.n - 1) / bx.n;
+    p.tdim[4] = p.tdim[5] = 1;
+    p.kdim[0] = (Cin + kBlockK - 1) / kBlockK;
+    p.kdim[1] = KW;
+    p.kdim[2] = KH;
+    p.ksplit_var = -1;
+    // A: activations, K-major pixel box with tap shifts
+    {
+        TmaOperand& a = p.a;
+        const uint64_t dims[4] = {uint64_t(Cin), uint64_t(W), uint64_t(H), uint64_t(N)};
+        const uint64_t str[3] = {uint64_t(Cin) * 2, uint64_t(W) * Cin * 2, uint64_t(H) * W * Cin * 2};
+        const uint32_t box[4] = {64, uint32_t(bx.w * stride), uint32_t(bx.h * stride), uint32_t(bx.n)};
+        const uint32_t est[4] = {1, uint32_t(stride), uint32_t(stride), 1};
+        if (int r = encode_tmap_bf16(&a.map, x, 4, dims, str, box, est)) return fail(r, "conv_fwd: A tensor map (%d)", r);
+        a.rank = 4; a.nbox = 1; a.box_dim = 0; a.box_step = 0; a.box_bytes = bx.w * bx.h * bx.n * 128;
+        a.base[1] = -pad_w0; a.base[2] = -pad_h0;
+        a.tcoef[1][1] = bx.w * stride; a.tcoef[2][2] = bx.h * stride; a.tcoef[3][3] = bx.n;
+        a.kcoef[0][0] = kBlockK; a.kcoef[1][1] = 1; a.kcoef[2][2] = 1;
+    }
+    // B: weights [Cout][KH*KW*Cin], K-major rows
+    {
+        TmaOperand& b = p.b;
+        const uint64_t kt = uint64_t(KH) * KW * Cin;
+        const uint64_t dims[2] = {kt, uint64_t(Cout)};
+        const uint64_t str[1] = {kt * 2};
+        const uint32_t box[2] = {64, uint32_t(p.block_n)};
+        if (int r = encode_tmap_bf16(&b.map, w, 2, dims, str, box, nullptr)) return fail(r, "conv_fwd: B tensor map (%d)", r);
+        b.rank = 2; b.nbox = 1; b.box_bytes = p.block_n * 128;
+        b.tcoef[1][0] = p.block_n;
+        b.kcoef[0][0] = kBlockK; b.kcoef[0][1] = Cin; b.kcoef[0][2] = KW * Cin;
+    }
+    finish_common(p, false);
+    p.bw = bx.w; p.bh = bx.h; p.bn = bx.n;
+    p.W = Wo; p.H = Ho; p.N = N; p.ncols = Cout;
+    p.ldw = Cout; p.ldh = int64_t(Wo) * Cout; p.ldn = int64_t(Ho) * Wo * Cout;
+    p.rb_ld = Cout;
+    fill_epilogue(p, epi, y, OUT_BF16);
+    set_vec_flag(p);
+    return launch_checked(launch_gemm(p, false, false, static_cast<cudaStream_t>(stream)), "conv_fwd");
+}
+
+int t2v_conv_dgrad(const void* dy, const void* w, void* dx, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                   int32_t KH, int32_t KW, int32_t stride, int32_t pad_h0, int32_t pad_h1, int32_t pad_w0,
+                   int32_t pad_w1, const T2VEpilogue* epi, void* stream) {
+    if (int r = check_channels(Cin, "Cin")) return r;
+    if (int r = check_channels(Cout, "Cout")) return r;
+    if (stride != 1 && stride != 2) return fail(-2, "conv_dgrad: stride %d unsupported", stride);
+    const int Ho = (H + pad_h0 + pad_h1 - KH) / stride + 1, Wo = (W + pad_w0 + pad_w1 - KW) / stride + 1;
+    const int s = stride;
+    // One launch per output parity class (a single class when stride == 1).
+    for (int ph = 0; ph < s; ++ph) {
+        for (int pw = 0; pw < s; ++pw) {
+            const int Hc = (H - ph + s - 1) / s, Wc = (W - pw + s - 1) / s;  // outputs in this class
+            if (Hc <= 0 || Wc <= 0) continue;
+            const int th0 = (ph + pad_h0) % s, tw0 = (pw + pad_w0) % s;      // first contributing tap
+            const int nth = th0 < KH ? (KH - th0 + s - 1) / s : 0, ntw = tw0 < KW ? (KW - tw0 + s - 1) / s : 0;
+            if (nth == 0 || ntw == 0) return fail(-2, "conv_dgrad: parity class without taps is unsupported");
+            GemmParams p;
+            std::memset(&p, 0, sizeof(p));
+            const Box3 bx = choose_pixel_box(kBlockM, Wc, Hc, N);
+            const int64_t row_tiles = int64_t((Wc + bx.w - 1) / bx.w) * ((Hc + bx.h - 1) / bx.h) * ((N + bx.n - 1) / bx.n);
+            p.block_n = choose_block_n(row_tiles, Cin, true);
+            p.tdim[0] = (Cin + p.block_n - 1) / p.block_n;
+            p.tdim[1] = (Wc + bx.w - 1) / bx.w;
+            p.tdim[2] = (Hc + bx.h - 1) / bx.h;
+            p.tdim[3] = (N + bx.n - 1) / bx.n;
+            p.tdim[4] = p.tdim[5] = 1;
+            p.kdim[0] = (Cout + kBlockK - 1) / kBlockK;
+            p.kdim[1] = ntw;
+            p.kdim[2] = nth;
+            p.ksplit_var = -1;
+            {
+                TmaOperand& a = p.a;  // dy, K-major (K = Cout), pixel box shifted against the tap
+                const uint64_t dims[4] = {uint64_t(Cout), uint64_t(Wo), uint64_t(Ho), uint64_t(N)};
+                const uint64_t str[3] = {uint64_t(Cout) * 2, uint64_t(Wo) * Cout * 2, uint64_t(Ho) * Wo * Cout * 2};
+                const uint32_t box[4] = {64, uint32_t(bx.w), uint32_t(bx.h), uint32_t(bx.n)};
+                if (int r = encode_tmap_bf16(&a.map, dy, 4, dims, str, box, nullptr)) return fail(r, "conv_dgrad: A tensor map (%d)", r);
+                a.rank = 4; a.nbox = 1; a.box_bytes = bx.w * bx.h * bx.n * 128;
+                a.base[1] = (pw + pad_w0 - tw0) / s; a.base[2] = (ph + pad_h0 - th0) / s;
+                a.tcoef[1][1] = bx.w; a.tcoef[2][2] = bx.h; a.tcoef[3][3] = bx.n;
+                a.kcoef[0][0] = kBlockK; a.kcoef[1][1] = -1; a.kcoef[2][2] = -1;
+            }
+            {
+                TmaOperand& b = p.b;  // w viewed as [Cout (k)][tap][Cin (n, contiguous)] -> MN-major
+                const uint64_t dims[3] = {uint64_t(Cin), uint64_t(KH) * KW, uint64_t(Cout)};
+                const uint64_t str[2] = {uint64_t(Cin) * 2, uint64_t(KH) * KW * Cin * 2};
+                const uint32_t box[3] = {64, 1, 64};
+                if (int r = encode_tmap_bf16(&b.map, w, 3, dims, str, box, nullptr)) return fail(r, "conv_dgrad: B tensor map (%d)", r);
+                b.rank = 3; b.nbox = (p.block_n + 63) / 64; b.box_dim = 0; b.box_step = 64; b.box_bytes = 8192;
+                b.base[1] = th0 * KW + tw0;
+                b.tcoef[0][0] = p.block_n;
+                b.kcoef[1][1] = s; b.kcoef[1][2] = s * KW; b.kcoef[2][0] = kBlockK;
+            }
+            finish_common(p, true);
+            p.bw = bx.w; p.bh = bx.h; p.bn = bx.n;
+            p.W = Wc; p.H = Hc; p.N = N; p.ncols = Cin;
+            p.ldw = int64_t(s) * Cin; p.ldh = int64_t(s) * W * Cin; p.ldn = int64_t(H) * W * Cin;
+            p.rb_ld = Cin;
+            const int64_t base_off = (int64_t(ph) * W + pw) * Cin;
+            T2VEpilogue e = epi ? *epi : T2VEpilogue{nullptr, nullptr, nullptr, 1.0f, 0};
+            const size_t esz = e.out_fp32 ? 4 : 2;
+            fill_epilogue(p, &e, static_cast<char*>(dx) + base_off * esz, OUT_BF16);
+            if (p.residual) p.residual = static_cast<const char*>(p.residual) + base_off * 2;
+            set_vec_flag(p);
+            if (int r = launch_checked(launch_gemm(p, false, true, static_cast<cudaStream_t>(stream)), "conv_dgrad")) return r;
+        }
+    }
+    return 0;
+}
+
+int t2v_conv_wgrad(const void* x, const void* dy, float* dw, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                   int32_t KH, int32_t KW, int32_t stride, int32_t pad_h0, int32_t pad_h1, int32_t pad_w0,
+                   int32_t pad_w1, void* stream) {
+    if (int r = check_channels(Cin, "Cin")) return r;
+    if (int r = check_channels(Cout, "Cout")) return r;
+    if (stride != 1 && stride != 2) return fail(-2, "conv_wgrad: stride %d unsupported", stride);
+    const int Ho = (H + pad_h0 + pad_h1 - KH) / stride + 1, Wo = (W + pad_w0 + pad_w1 - KW) / stride + 1;
+    GemmParams p;
+    std::memset(&p, 0, sizeof(p));
+    const Box3 kx = choose_pixel_box(kBlockK, Wo, Ho, N);  // 64 output pixels per k-block
+    const int64_t row_tiles = int64_t((Cout + kBlockM - 1) / kBlockM) * KH * KW;
+    p.block_n = choose_block_n(row_tiles, Cin, true);
+    p.kdim[0] = (Wo + kx.w - 1) / kx.w;
+    p.kdim[1] = (Ho + kx.h - 1) / kx.h;
+    p.kdim[2] = (N + kx.n - 1) / kx.n;
+    const int kb_total = p.kdim[0] * p.kdim[1] * p.kdim[2];
+    p.tdim[0] = (Cin + p.block_n - 1) / p.block_n;
+    p.tdim[1] = (Cout + kBlockM - 1) / kBlockM;
+    p.tdim[2] = KW;
+    p.tdim[3] = KH;
+    const int64_t base_tiles = int64_t(p.tdim[0]) * p.tdim[1] * KW * KH;
+    int splits = static_cast<int>(std::min<int64_t>(kb_total, std::max<int64_t>(1, (2 * device_sm_count() + base_tiles - 1) / base_tiles)));
+    p.kb_per_split = (kb_total + splits - 1) / splits;
+    splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
+    p.tdim[4] = splits;
+    p.tdim[5] = 1;
+    p.ksplit_var = 4;
+    {
+        TmaOperand& a = p.a;  // dy^T: M = Cout (contiguous), K = pixels -> MN-major, two 64-wide boxes
+        const uint64_t dims[4] = {uint64_t(Cout), uint64_t(Wo), uint64_t(Ho), uint64_t(N)};
+        const uint64_t str[3] = {uint64_t(Cout) * 2, uint64_t(Wo) * Cout * 2, uint64_t(Ho) * Wo * Cout * 2};
+        const uint32_t box[4] = {64, uint32_t(kx.w), uint32_t(kx.h), uint32_t(kx.n)};
+        if (int r = encode_tmap_bf16(&a.map, dy, 4, dims, str, box, nullptr)) return fail(r, "conv_wgrad: A tensor map (%d)", r);
+        a.rank = 4; a.nbox = 2; a.box_dim = 0; a.box_step = 64; a.box_bytes = 8192;
+        a.tcoef[0][1] = kBlockM;
+        a.kcoef[1][0] = kx.w; a.kcoef[2][1] = kx.h; a.kcoef[3][2] = kx.n;
+    }
+    {
+        TmaOperand& b = p.b;  // x shifted by the tap: N = Cin (contiguous), K = pixels -> MN-major
+        const uint64_t dims[4] = {uint64_t(Cin), uint64_t(W), uint64_t(H), uint64_t(N)};
+        const uint64_t str[3] = {uint64_t(Cin) * 2, uint64_t(W) * Cin * 2, uint64_t(H) * W * Cin * 2};
+        const uint32_t box[4] = {64, uint32_t(kx.w * stride), uint32_t(kx.h * stride), uint32_t(kx.n)};
+        const uint32_t est[4] = {1, uint32_t(stride), uint32_t(stride), 1};
+        if (int r = encode_tmap_bf16(&b.map, x, 4, dims, str, box, est)) return fail(r, "conv_wgrad: B tensor map (%d)", r);
+        b.rank = 4; b.nbox = (p.block_n + 63) / 64; b.box_dim = 0; b.box_step = 64; b.box_bytes = 8192;
+        b.base[1] = -pad_w0; b.base[2] = -pad_h0;
+        b.tcoef[0][0] = p.block_n; b.tcoef[1][2] = 1; b.tcoef[2][3] = 1;
+        b.kcoef[1][0] = kx.w * stride; b.kcoef[2][1] = kx.h * stride; b.kcoef[3][2] = kx.n;
+    }
+    finish_common(p, true);
+    p.bw = kBlockM; p.bh = 1; p.bn = 1;
+    p.W = Cout; p.H = KW; p.N = KH; p.ncols = Cin;
+    p.ldw = int64_t(KH) * KW * Cin; p.ldh = Cin; p.ldn = int64_t(KW) * Cin;
+    fill_epilogue(p, nullptr, dw, OUT_F32_RED);
+    p.alpha = 1.0f;
+    set_vec_flag(p);
+    return launch_checked(launch_gemm(p, true, true, static_cast<cudaStream_t>(stream)), "conv_wgrad");
+}
+
+int t2v_bgemm(const T2VMat* A, const T2VMat* B, void* C, int64_t ldc, int64_t c_stride_z1, int64_t c_stride_z2,
+              int32_t M, int32_t N, int32_t K, int32_t Z1, int32_t Z2, float alpha, int32_t out_mode, void* stream) {
+    if (M <= 0 || N <= 0 || K <= 0 || Z1 <= 0 || Z2 <= 0) return fail(-2, "bgemm: bad shape");
+    if (A->ld % 8 || B->ld % 8) return fail(-2, "bgemm: leading dimensions must be multiples of 8 elements");
+    if ((Z1 > 1 && (A->stride_z1 % 8 || B->stride_z1 % 8)) || (Z2 > 1 && (A->stride_z2 % 8 || B->stride_z2 % 8)))
+        return fail(-2, "bgemm: batch strides must be multiples of 8 elements");
+    const bool a_mn = !A->kmajor, b_mn = !B->kmajor;
+    GemmParams p;
+    std::memset(&p, 0, sizeof(p));
+    const int64_t row_tiles = int64_t((M + kBlockM - 1) / kBlockM) * Z1 * Z2;
+    p.block_n = choose_block_n(row_tiles, N, b_mn);
+    p.kdim[0] = (K + kBlockK - 1) / kBlockK;
+    p.kdim[1] = p.kdim[2] = 1;
+    p.tdim[0] = (N + p.block_n - 1) / p.block_n;
+    p.tdim[1] = (M + kBlockM - 1) / kBlockM;
+    p.tdim[2] = 1;
+    p.tdim[3] = 1;
+    p.tdim[4] = Z2;
+    p.tdim[5] = Z1;
+    p.ksplit_var = -1;
+    int splits = 1;
+    if (out_mode == OUT_F32_RED) {
+        const int64_t base_tiles = int64_t(p.tdim[0]) * p.tdim[1] * Z1 * Z2;
+        splits = static_cast<int>(std::min<int64_t>(p.kdim[0], std::max<int64_t>(1, (2 * device_sm_count() + base_tiles - 1) / base_tiles)));
+        p.kb_per_split = (p.kdim[0] + splits - 1) / splits;
+        splits = (p.kdim[0] + p.kb_per_split - 1) / p.kb_per_split;
+        p.tdim[2] = splits;
+        p.ksplit_var = 2;
+    }
+    auto stride_or = [](int64_t s, int64_t fallback) { return uint64_t((s > 0 ? s : fallback) * 2); };
+    auto plan_operand = [&](TmaOperand& op, const T2VMat* m, bool mn, int rows_mn, int block_mn, int tile_var) -> int {
+        // stored matrix: K-major [rows_mn][K]; MN-major [K][rows_mn]
+        const uint64_t inner = mn ? uint64_t(rows_mn) : uint64_t(K), outer = mn ? uint64_t(K) : uint64_t(rows_mn);
+        const uint64_t dims[4] = {inner, outer, uint64_t(Z2), uint64_t(Z1)};
+        const uint64_t str[3] = {uint64_t(m->ld) * 2, stride_or(m->stride_z2, m->ld * int64_t(outer)),
+                                 stride_or(m->stride_z1, m->ld * int64_t(outer) * Z2)};
+        const uint32_t box[4] = {64, uint32_t(mn ? 64 : block_mn), 1, 1};
+        if (int r = encode_tmap_bf16(&op.map, m->ptr, 4, dims, str, box, nullptr)) return r;
+        op.rank = 4;
+        op.tcoef[2][4] = 1;
+        op.tcoef[3][5] = 1;
+        if (mn) {
+            op.nbox = (block_mn + 63) / 64; op.box_dim = 0; op.box_step = 64; op.box_bytes = 8192;
+            op.tcoef[0][tile_var] = block_mn;
+            op.kcoef[1][0] = kBlockK;
+        } else {
+            op.nbox = 1; op.box_bytes = block_mn * 128;
+            op.tcoef[1][tile_var] = block_mn;
+            op.kcoef[0][0] = kBlockK;
+        }
+        return 0;
+    };
+    if (int r = plan_operand(p.a, A, a_mn, M, kBlockM, 1)) return fail(r, "bgemm: A tensor map (%d)", r);
+    if (int r = plan_operand(p.b, B, b_mn, N, p.block_n, 0)) return fail(r, "bgemm: B tensor map (%d)", r);
+    finish_common(p, b_mn);
+    p.bw = kBlockM; p.bh = 1; p.bn = 1;
+    p.W = M; p.H = splits; p.N = 1; p.ncols = N;
+    p.ldw = ldc; p.ldh = 0; p.ldn = 0;
+    p.otc[4] = c_stride_z2; p.otc[5] = c_stride_z1;
+    T2VEpilogue e{nullptr, nullptr, nullptr, alpha, out_mode != OUT_BF16};
+    fill_epilogue(p, &e, C, OUT_BF16);
+    p.out_mode = out_mode;
+    set_vec_flag(p);
+    return launch_checked(launch_gemm(p, a_mn, b_mn, static_cast<cudaStream_t>(stream)), "bgemm");
+}
+
+}  // extern "C"

@@ -1,0 +1,349 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a.  See gemm_tc.cuh for the operand model.
+//
+//   warp 0 : TMA producer   (one elected lane) - fills the smem ring, one mbarrier pair per stage
+//   warp 1 : MMA issuer     (one elected lane) - tcgen05.mma into one of two TMEM accumulator stages
+//   warps 2-5 : epilogue    (128 threads, thread <-> accumulator row) - tcgen05.ld, fused epilogue, global stores
+//
+// The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
+#include "gemm_tc.cuh"
+#include "ptx.cuh"
+
+#include <cstdio>
+#include <mutex>
+
+namespace t2v {
+
+struct TileVars {
+    int32_t t[6];
+};
+
+__device__ __forceinline__ void decompose_tile(const GemmParams& p, int32_t tile, TileVars& tv) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int32_t d = p.tdim[i];
+        tv.t[i] = tile % d;
+        tile /= d;
+    }
+}
+
+__device__ __forceinline__ void k_range(const GemmParams& p, const TileVars& tv, int32_t& kb0, int32_t& kb1) {
+    if (p.ksplit_var >= 0) {
+        kb0 = tv.t[p.ksplit_var] * p.kb_per_split;
+        kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+    } else {
+        kb0 = 0;
+        kb1 = p.kb_total;
+    }
+}
+
+__device__ __forceinline__ void tile_coords(const TmaOperand& op, const TileVars& tv, int32_t* c) {
+#pragma unroll
+    for (int d = 0; d < 5; ++d) {
+        int32_t v = op.base[d];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) v += tv.t[i] * op.tcoef[d][i];
+        c[d] = v;
+    }
+}
+
+__device__ __forceinline__ void issue_operand(const TmaOperand& op, const int32_t* tile_c, const int32_t* kv,
+                                              uint8_t* smem_dst, uint64_t* bar) {
+    int32_t c[5];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) c[d] = tile_c[d] + kv[0] * op.kcoef[d][0] + kv[1] * op.kcoef[d][1] + kv[2] * op.kcoef[d][2];
+    for (int b = 0; b < op.nbox; ++b) {
+        tma_load(op.rank, smem_dst + b * op.box_bytes, &op.map, bar, c);
+        c[op.box_dim] += op.box_step;
+    }
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment is required by the 128-byte swizzle atoms.
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int S = p.num_stages;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + static_cast<size_t>(S) * p.stage_bytes_a;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + static_cast<size_t>(S) * p.stage_bytes_b);
+    uint64_t* full_bar = bars;                       // [S]   TMA -> MMA
+    uint64_t* empty_bar = bars + kMaxStages;         // [S]   MMA -> TMA
+    uint64_t* acc_full = bars + 2 * kMaxStages;      // [2]   MMA -> epilogue
+    uint64_t* acc_empty = bars + 2 * kMaxStages + 2; // [2]   epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.a.map);
+        tma_prefetch_desc(&p.b.map);
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0;
+            const uint32_t tx_bytes = p.stage_bytes_a + p.stage_bytes_b;
+            for (int32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                TileVars tv;
+                decompose_tile(p, tile, tv);
+                int32_t ca[5], cb[5];
+                tile_coords(p.a, tv, ca);
+                tile_coords(p.b, tv, cb);
+                int32_t kb0, kb1;
+                k_range(p, tv, kb0, kb1);
+                for (int32_t kb = kb0; kb < kb1; ++kb) {
+                    int32_t kv[3];
+                    int32_t r = kb;
+                    kv[0] = r % p.kdim[0];
+                    r /= p.kdim[0];
+                    kv[1] = r % p.kdim[1];
+                    kv[2] = r / p.kdim[1];
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], tx_bytes);
+                    issue_operand(p.a, ca, kv, smem_a + static_cast<size_t>(stage) * p.stage_bytes_a, &full_bar[stage]);
+                    issue_operand(p.b, cb, kv, smem_b + static_cast<size_t>(stage) * p.stage_bytes_b, &full_bar[stage]);
+                    if (++stage == static_cast<uint32_t>(S)) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(static_cast<uint32_t>(p.block_n), A_MN, B_MN);
+            // descriptor advance per UMMA_K=16 step, in 16-byte units
+            constexpr uint32_t a_kstep = A_MN ? (16u * 128u) >> 4 : 32u >> 4;
+            constexpr uint32_t b_kstep = B_MN ? (16u * 128u) >> 4 : 32u >> 4;
+            constexpr uint32_t a_lbo = A_MN ? 64u * 128u : 0u;
+            constexpr uint32_t b_lbo = B_MN ? 64u * 128u : 0u;
+            uint32_t stage = 0, phase = 0;
+            uint32_t it = 0;
+            for (int32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                TileVars tv;
+                decompose_tile(p, tile, tv);
+                int32_t kb0, kb1;
+                k_range(p, tv, kb0, kb1);
+                const uint32_t as = it & 1u;
+                const uint32_t aphase = (it >> 1) & 1u;
+                mbar_wait(&acc_empty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * 256u;
+                for (int32_t kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = make_sw128_desc(smem_u32(smem_a + static_cast<size_t>(stage) * p.stage_bytes_a), a_lbo, 1024);
+                    const uint64_t db = make_sw128_desc(smem_u32(smem_b + static_cast<size_t>(stage) * p.stage_bytes_b), b_lbo, 1024);
+#pragma unroll
+                    for (uint32_t k = 0; k < kBlockK / 16; ++k) {
+                        umma_f16(tmem_d, da + k * a_kstep, db + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
+                    if (++stage == static_cast<uint32_t>(S)) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&acc_full[as]);  // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const uint32_t quad = warp & 3u;  // TMEM lane quadrant this warp may access
+        const uint32_t row = quad * 32u + lane;
+        const int32_t rw = static_cast<int32_t>(row) % p.bw;
+        const int32_t rh = (static_cast<int32_t>(row) / p.bw) % p.bh;
+        const int32_t rn = static_cast<int32_t>(row) / (p.bw * p.bh);
+        const bool has_bias = p.flags & EPI_BIAS, has_rb = p.flags & EPI_ROWBIAS, has_res = p.flags & EPI_RESIDUAL;
+        const bool vec = p.flags & EPI_VEC;
+        uint32_t it = 0;
+        for (int32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            TileVars tv;
+            decompose_tile(p, tile, tv);
+            const int32_t gw = tv.t[1] * p.bw + rw, gh = tv.t[2] * p.bh + rh, gn = tv.t[3] * p.bn + rn;
+            const bool row_ok = (rn < p.bn) && gw < p.W && gh < p.H && gn < p.N;
+            int64_t off = gw * p.ldw + gh * p.ldh + gn * p.ldn;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) off += tv.t[i] * p.otc[i];
+            const int32_t col0 = tv.t[0] * p.block_n;
+            const uint32_t as = it & 1u;
+            const uint32_t aphase = (it >> 1) & 1u;
+            mbar_wait(&acc_full[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + as * 256u;
+            for (int32_t c0 = 0; c0 < p.block_n; c0 += 16) {
+                uint32_t r[16];
+                __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent stores below
+                tmem_ld16(taddr + c0, r);
+                tmem_ld_wait();
+                const int32_t col = col0 + c0;
+                if (!row_ok || col >= p.ncols) continue;
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+                const bool full = vec && (col + 16 <= p.ncols);
+                if (full) {
+                    if (has_bias) {
+                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 b = __ldg(b4 + j);
+                            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                        }
+                    }
+                    if (has_rb) {
+                        const float4* b4 = reinterpret_cast<const float4*>(p.rowbias + gn * p.rb_ld + col);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 b = __ldg(b4 + j);
+                            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                        }
+                    }
+                    if (has_res) {
+                        const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + off + col);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const uint4 q = __ldg(r4 + j);
+                            v[8 * j + 0] += bf16_lo(q.x); v[8 * j + 1] += bf16_hi(q.x);
+                            v[8 * j + 2] += bf16_lo(q.y); v[8 * j + 3] += bf16_hi(q.y);
+                            v[8 * j + 4] += bf16_lo(q.z); v[8 * j + 5] += bf16_hi(q.z);
+                            v[8 * j + 6] += bf16_lo(q.w); v[8 * j + 7] += bf16_hi(q.w);
+                        }
+                    }
+                    if (p.out_mode == OUT_BF16) {
+                        uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + off + col);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            uint4 q;
+                            q.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+                            q.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+                            q.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+                            q.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+                            o4[j] = q;
+                        }
+                    } else if (p.out_mode == OUT_F32) {
+                        float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(p.out) + off + col);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    } else {
+                        float* o = static_cast<float*>(p.out) + off + col;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) red_add_f32x4(o + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                } else {
+                    // scalar tail / unaligned path
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (col + j >= p.ncols) break;
+                        float x = v[j];
+                        if (has_bias) x += p.bias[col + j];
+                        if (has_rb) x += p.rowbias[gn * p.rb_ld + col + j];
+                        if (has_res) x += __bfloat162float(static_cast<const __nv_bfloat16*>(p.residual)[off + col + j]);
+                        if (p.out_mode == OUT_BF16) static_cast<__nv_bfloat16*>(p.out)[off + col + j] = __float2bfloat16_rn(x);
+                        else if (p.out_mode == OUT_F32) static_cast<float*>(p.out)[off + col + j] = x;
+                        else atomicAdd(static_cast<float*>(p.out) + off + col + j, x);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[as]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+
+static int g_sm_count = 0;
+int device_sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sm_count <= 0) g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    });
+    return fn;
+}
+
+int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                     const uint32_t* box, const uint32_t* elem_strides) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return -1;
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bdim[5], estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estr[i] = elem_strides ? elem_strides[i] : 1;
+    }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides[i];
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
+                    gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
+}
+
+template <bool A_MN, bool B_MN>
+static int launch_impl(const GemmParams& p, cudaStream_t stream) {
+    static bool attr_set = false;
+    const size_t smem = static_cast<size_t>(p.num_stages) * (p.stage_bytes_a + p.stage_bytes_b) + 1024 /*align*/ + 256 /*barriers*/;
+    auto kern = gemm_tc_kernel<A_MN, B_MN>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        attr_set = true;
+    }
+    int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
+    if (grid < 1) return 0;
+    kern<<<grid, kNumThreads, smem, stream>>>(p);
+    return static_cast<int>(cudaGetLastError());
+}
+
+int launch_gemm(const GemmParams& p, bool a_mn, bool b_mn, cudaStream_t stream) {
+    if (!a_mn && !b_mn) return launch_impl<false, false>(p, stream);
+    if (!a_mn && b_mn) return launch_impl<false, true>(p, stream);
+    if (a_mn && b_mn) return launch_impl<true, true>(p, stream);
+    return launch_impl<true, false>(p, stream);
+}
+
+}  // namespace t2v

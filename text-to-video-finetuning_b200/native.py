@@ -1,0 +1,97 @@
+"""ctypes binding of the C ABI (include/t2v_b200.h) + in-tree build of the sm_100a shared library.
+
+There is deliberately no fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_DIR = os.path.join(_HERE, "_native")
+LIB_PATH = os.path.join(LIB_DIR, "libt2v_b200.so")
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "--use_fast_math", "-shared",
+]
+
+_lib = None
+_lock = threading.Lock()
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(_HERE, "..", "include", "t2v_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu for sm_100a into _native/libt2v_b200.so (nvcc cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    nvcc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + sources()
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+class Epilogue(ctypes.Structure):
+    _fields_ = [("bias", ctypes.c_void_p), ("rowbias", ctypes.c_void_p), ("residual", ctypes.c_void_p),
+                ("alpha", ctypes.c_float), ("out_fp32", ctypes.c_int32)]
+
+
+class Mat(ctypes.Structure):
+    _fields_ = [("ptr", ctypes.c_void_p), ("ld", ctypes.c_int64), ("stride_z1", ctypes.c_int64),
+                ("stride_z2", ctypes.c_int64), ("kmajor", ctypes.c_int32)]
+
+
+def _declare(lib):
+    i32, i64, vp, f32 = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_float
+    lib.t2v_version.restype = i32
+    lib.t2v_last_error.restype = ctypes.c_char_p
+    lib.t2v_launch_count.restype = i64
+    conv_args = [vp, vp, vp] + [i32] * 12
+    lib.t2v_conv_fwd.argtypes = conv_args + [ctypes.POINTER(Epilogue), vp]
+    lib.t2v_conv_dgrad.argtypes = conv_args + [ctypes.POINTER(Epilogue), vp]
+    lib.t2v_conv_wgrad.argtypes = conv_args + [vp]
+    lib.t2v_bgemm.argtypes = [ctypes.POINTER(Mat), ctypes.POINTER(Mat), vp, i64, i64, i64, i32, i32, i32, i32, i32, f32, i32, vp]
+    for name in dir(lib):
+        pass
+    return lib
+
+
+def lib():
+    """Returns the loaded library; raises if it has not been built (no CPU fallback exists)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(the sm_100a CUDA extension is the only implementation of this path)")
+                _lib = _declare(ctypes.CDLL(LIB_PATH))
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError(f"t2v_b200 native call failed ({rc}): {lib().t2v_last_error().decode()}")
+
+
+def launch_count():
+    return int(lib().t2v_launch_count())
