@@ -44,6 +44,8 @@ typedef struct {
     const void* residual;   /* bf16, same shape/layout as the output, or NULL                             */
     float alpha;
     int32_t out_fp32;       /* 0: bf16 output, 1: fp32 output                                             */
+    int32_t rowbias_div;    /* rowbias row = n / rowbias_div (frames per clip: one time-embedding row per
+                               clip instead of the reference's repeat_interleave, unet_3d_condition.py:400) */
 } T2VEpilogue;
 
 /* Implicit-GEMM convolution forward on tcgen05 tensor cores (TMA-fed, zero padding by TMA OOB fill).
@@ -85,6 +87,81 @@ typedef struct {
 } T2VMat;
 int t2v_bgemm(const T2VMat* A, const T2VMat* B, void* C, int64_t ldc, int64_t c_stride_z1, int64_t c_stride_z2,
               int32_t M, int32_t N, int32_t K, int32_t Z1, int32_t Z2, float alpha, int32_t out_mode, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * HBM-bound kernels (128-bit accesses, fp32 statistics, warp-shuffle reductions).
+ */
+
+/* GroupNorm (+ fused SiLU) over x [S][P][C] bf16: S normalisation samples of P pixels; replaces nn.GroupNorm + SiLU in
+ * ResnetBlock2D.norm1/norm2 (per frame: S = B*F), Transformer2DModel.norm (eps 1e-6), TemporalConvLayer /
+ * TransformerTemporalModel.norm (per clip: S = B, P = F*H*W) and conv_norm_out (unet_3d_condition.py:239-243,488-490).
+ * stat [S][G][2] = (mean, rstd), ab [S][C][2] = per-channel affine with y = act(a x + b) (both saved for backward).
+ * workspace: t2v_groupnorm_workspace_bytes(S, P, C) bytes.                                                        */
+int64_t t2v_groupnorm_workspace_bytes(int32_t S, int64_t P, int32_t C);
+int t2v_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stat, float* ab, void* workspace,
+                      int32_t S, int64_t P, int32_t C, int32_t G, float eps, int32_t silu, void* stream);
+/* dx = d/dx [act(GN(x))]^T dy (+ add); dgamma / dbeta (fp32) are accumulated (+=) and may be NULL.               */
+int t2v_groupnorm_bwd(const void* dy, const void* x, const float* gamma, const float* stat, const float* ab, const void* add,
+                      void* dx, float* dgamma, float* dbeta, void* workspace, int32_t S, int64_t P, int32_t C, int32_t G,
+                      int32_t silu, void* stream);
+
+/* LayerNorm over rows of x [rows][C] (BasicTransformerBlock.norm1/2/3, eps 1e-5); stat [rows][2] = (mean, rstd).  */
+int t2v_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stat, int64_t rows, int32_t C,
+                      float eps, void* stream);
+int t2v_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* stat, const void* add, void* dx,
+                      float* dgamma, float* dbeta, int64_t rows, int32_t C, void* stream);
+
+/* Latent boundary.  (B, C<=8, F, H, W) fp32 -> [B*F][H*W][8] bf16 with zero-padded channels; when `noise` is given this
+ * is DDPMScheduler.add_noise fused in: x_t = sqrt(abar[t_b]) x0 + sqrt(1 - abar[t_b]) eps  (train.py:751-760) and the
+ * permute/reshape of unet_3d_condition.py:404.  nhwc8_to_latents is the inverse (unet_3d_condition.py:495).        */
+int t2v_latents_to_nhwc8(const float* x0, const float* noise, const float* alphas_cumprod, const int64_t* timesteps, void* out,
+                         int32_t B, int32_t C, int32_t F, int32_t HW, void* stream);
+int t2v_nhwc8_to_latents(const void* in, float* out, int32_t B, int32_t C, int32_t F, int32_t HW, void* stream);
+/* F.mse_loss(pred.float(), target.float()) (train.py:827) straight from the channels-last prediction.
+ * loss != NULL: *loss = mean((pred - target)^2).  dpred != NULL: dpred = *gout * 2 (pred - target) / numel.         */
+int t2v_mse_loss(const void* pred, const float* target, float* loss, const float* gout, void* dpred, int32_t B, int32_t C,
+                 int32_t F, int32_t HW, void* stream);
+
+/* GEGLU (diffusers FeedForward.net[0]): proj [M][2I] -> out [M][I] = h * gelu_erf(gate).                           */
+int t2v_geglu_fwd(const void* proj, void* out, int64_t M, int32_t I, void* stream);
+int t2v_geglu_bwd(const void* proj, const void* dout, void* dproj, int64_t M, int32_t I, void* stream);
+
+/* SiLU on the (tiny) time-embedding path, casts, scaled copies and gradient fan-in adds.                           */
+int t2v_silu_f32_to_bf16(const float* x, void* y, int64_t n, int32_t apply_silu, void* stream);
+int t2v_silu_bwd_f32(const float* x, const float* dy, float* dx, int64_t n, int32_t accumulate, void* stream);
+int t2v_silu_bf16(const void* x, void* y, int64_t n, void* stream);
+int t2v_silu_bf16_bwd(const void* x, const void* dy, void* dx, int64_t n, void* stream);
+int t2v_add_bf16(const void* a, const void* b, const void* c, void* out, int64_t n, void* stream);
+int t2v_scale_bf16(const void* a, void* out, int64_t n, float alpha, void* stream);
+int t2v_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream);
+int t2v_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+/* Upsample2D's F.interpolate(mode="nearest") on [N][H][W][C] and its gradient (any size ratio).                      */
+int t2v_upsample_nearest_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t Ho, int32_t Wo, int32_t C, void* stream);
+int t2v_upsample_nearest_bwd(const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t Ho, int32_t Wo, int32_t C, void* stream);
+/* Channel-range copy between row-major bf16 matrices: the skip-connection torch.cat / its split in backward
+ * (unet_3d_blocks.py:764,861).                                                                                     */
+int t2v_copy_cols(const void* src, void* dst, int64_t M, int32_t C, int32_t src_ld, int32_t src_off, int32_t dst_ld, int32_t dst_off,
+                  void* stream);
+/* out [S][C] (fp32) += sum_p x [S][P][C]: bias gradients and the per-clip time-embedding gradient.                 */
+int t2v_colsum(const void* x, float* out, int32_t S, int64_t P, int32_t C, void* stream);
+int t2v_colsum_f32(const float* x, float* out, int32_t S, int32_t C, void* stream);
+/* Row softmax between the two attention GEMMs: fp32 scores [rows][ld_in] -> bf16 probabilities [rows][ld_out]
+ * (columns >= n_valid written as 0), and dS = P * (dP - rowsum(P dP)) * scale.                                     */
+int t2v_softmax_fwd(const float* s, void* p, int64_t rows, int32_t n_valid, int32_t ld_in, int32_t ld_out, void* stream);
+int t2v_softmax_bwd(const void* p, const float* dp, void* ds, int64_t rows, int32_t n_valid, int32_t ld_p, int32_t ld_dp, float scale,
+                    void* stream);
+/* Timesteps(dim, flip_sin_to_cos=True, shift 0) (unet_3d_condition.py:138,392): int64 [B] -> bf16 [B][dim] = [cos | sin]. */
+int t2v_timestep_embedding(const int64_t* t, void* out, int32_t B, int32_t dim, void* stream);
+
+/* Self-attention over short sequences (L <= 32, head_dim 32 or 64) addressed by strides: the frame-axis attention of
+ * TransformerTemporalModel (unet_3d_condition.py:147-152; unet_3d_blocks.py:331-340) without its permutes.
+ * token t of sequence z, head h lives at  (z / inner) * outer_stride + (z % inner) * inner_stride + t * seq_stride + h * D. */
+int t2v_attn_small_fwd(const void* q, const void* k, const void* v, void* o, int64_t nseq, int32_t inner, int64_t outer_stride,
+                       int64_t inner_stride, int64_t seq_stride, int32_t heads, int32_t L, int32_t D, void* stream);
+int t2v_attn_small_bwd(const void* q, const void* k, const void* v, const void* dout, void* dq, void* dk, void* dv, int64_t nseq,
+                       int32_t inner, int64_t outer_stride, int64_t inner_stride, int64_t seq_stride, int32_t heads, int32_t L,
+                       int32_t D, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,314 @@
+"""ORACLE (test infrastructure): plain-PyTorch fp32 restatement of every primitive in
+text-to-video-finetuning_b200/prims.py, with identical signatures, tensor layouts and rounding points (bf16 storage
+between ops, fp32 math inside).  Two uses, both in tests only:
+  * per-kernel GPU parity tests compare each sm_100a kernel against the function of the same name here;
+  * CPU tests monkeypatch `prims` with this module to check the host-side wiring and the hand-written backward
+    composition in ops.py / layers.py against the model oracle, without a GPU.
+The product never imports this file (no CPU fallback exists in the product path).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+BF = torch.bfloat16
+
+
+def out_hw(H, W, KH, KW, stride, pads):
+    return (H + pads[0] + pads[1] - KH) // stride + 1, (W + pads[2] + pads[3] - KW) // stride + 1
+
+
+def _conv_f32(x, w, stride, pads):
+    xf = F.pad(x.float().permute(0, 3, 1, 2), (pads[2], pads[3], pads[0], pads[1]))
+    return F.conv2d(xf, w.float().permute(0, 3, 1, 2), stride=stride).permute(0, 2, 3, 1)
+
+
+def conv_fwd(x, w, bias=None, rowbias=None, residual=None, stride=1, pads=(0, 0, 0, 0), alpha=1.0, out_fp32=False, rowbias_div=1):
+    y = alpha * _conv_f32(x, w, stride, pads)
+    if bias is not None:
+        y = y + bias
+    if rowbias is not None:
+        idx = torch.arange(x.shape[0], device=x.device) // rowbias_div
+        y = y + rowbias[idx][:, None, None, :]
+    if residual is not None:
+        y = y + residual.float()
+    return y.contiguous() if out_fp32 else y.to(BF).contiguous()
+
+
+@torch.enable_grad()
+def conv_dgrad(dy, w, in_hw, stride=1, pads=(0, 0, 0, 0), residual=None):
+    N = dy.shape[0]
+    Co, KH, KW, Ci = w.shape
+    x = torch.zeros((N, in_hw[0], in_hw[1], Ci), dtype=torch.float32, device=dy.device, requires_grad=True)
+    y = _conv_f32(x, w, stride, pads)
+    (dx,) = torch.autograd.grad(y, x, dy.float())
+    if residual is not None:
+        dx = dx + residual.float()
+    return dx.to(BF).contiguous()
+
+
+@torch.enable_grad()
+def conv_wgrad(x, dy, dw, stride=1, pads=(0, 0, 0, 0)):
+    w = torch.zeros(dw.shape, dtype=torch.float32, device=x.device, requires_grad=True)
+    y = _conv_f32(x, w, stride, pads)
+    (g,) = torch.autograd.grad(y, w, dy.float())
+    dw += g
+
+
+def _strided(t, sizes, strides):
+    return torch.as_strided(t.reshape(-1), sizes, strides)
+
+
+def bgemm(a, a_desc, b, b_desc, c, c_desc, M, N, K, Z1, Z2, alpha=1.0, out_mode=0):
+    ak, ald, as1, as2 = a_desc
+    bk, bld, bs1, bs2 = b_desc
+    A = _strided(a, (Z1, Z2, M, K), (as1, as2, ald, 1)) if ak else _strided(a, (Z1, Z2, K, M), (as1, as2, ald, 1)).transpose(-1, -2)
+    B = _strided(b, (Z1, Z2, N, K), (bs1, bs2, bld, 1)) if bk else _strided(b, (Z1, Z2, K, N), (bs1, bs2, bld, 1)).transpose(-1, -2)
+    r = alpha * (A.float() @ B.float().transpose(-1, -2))
+    C = _strided(c, (Z1, Z2, M, N), (c_desc[1], c_desc[2], c_desc[0], 1))
+    if out_mode == 2:
+        C += r
+    else:
+        C.copy_(r.to(c.dtype))
+
+
+# ---------------------------------------------------------------------------------------------- norms
+def _gn_apply(x3, gamma, beta, G, eps, silu):
+    S, P, C = x3.shape
+    xf = x3.float().view(S, P, G, C // G)
+    mean = xf.mean(dim=(1, 3), keepdim=True)
+    var = xf.var(dim=(1, 3), unbiased=False, keepdim=True)
+    rstd = (var + eps).rsqrt()
+    y = ((xf - mean) * rstd).view(S, P, C) * gamma + beta
+    if silu:
+        y = F.silu(y)
+    return y, mean.view(S, G), rstd.view(S, G)
+
+
+def groupnorm_fwd(x, gamma, beta, G, eps, silu):
+    S, P, C = x.shape
+    y, mean, rstd = _gn_apply(x, gamma.float(), beta.float(), G, eps, silu)
+    stat = torch.stack([mean, rstd], dim=-1).contiguous()
+    cpg = C // G
+    a = rstd.repeat_interleave(cpg, dim=1) * gamma.float()
+    b = beta.float() - mean.repeat_interleave(cpg, dim=1) * a
+    return y.to(BF).contiguous(), stat, torch.stack([a, b], dim=-1).contiguous()
+
+
+def groupnorm_bwd(dy, x, gamma, stat, ab, G, silu, add=None, dgamma=None, dbeta=None):
+    S, P, C = x.shape
+    cpg = C // G
+    mean = stat[..., 0].repeat_interleave(cpg, dim=1)[:, None, :]
+    rstd = stat[..., 1].repeat_interleave(cpg, dim=1)[:, None, :]
+    xh = (x.float() - mean) * rstd
+    dz = dy.float()
+    if silu:
+        z = ab[..., 0][:, None, :] * x.float() + ab[..., 1][:, None, :]
+        sg = torch.sigmoid(z)
+        dz = dz * sg * (1 + z * (1 - sg))
+    if dgamma is not None:
+        dgamma += (dz * xh).sum(dim=(0, 1))
+    if dbeta is not None:
+        dbeta += dz.sum(dim=(0, 1))
+    dxh = (dz * gamma.float()).view(S, P, G, cpg)
+    xg = xh.view(S, P, G, cpg)
+    m1 = dxh.mean(dim=(1, 3), keepdim=True)
+    m2 = (dxh * xg).mean(dim=(1, 3), keepdim=True)
+    dx = (rstd.view(S, 1, G, cpg) * (dxh - m1 - xg * m2)).view(S, P, C)
+    if add is not None:
+        dx = dx + add.float()
+    return dx.to(BF).contiguous()
+
+
+def layernorm_fwd(x, gamma, beta, eps):
+    xf = x.float()
+    mean = xf.mean(-1, keepdim=True)
+    var = xf.var(-1, unbiased=False, keepdim=True)
+    rstd = (var + eps).rsqrt()
+    y = (xf - mean) * rstd * gamma.float() + beta.float()
+    return y.to(BF).contiguous(), torch.cat([mean, rstd], dim=-1).contiguous()
+
+
+def layernorm_bwd(dy, x, gamma, stat, add=None, dgamma=None, dbeta=None):
+    xf = x.float()
+    mean, rstd = stat[:, :1], stat[:, 1:]
+    xh = (xf - mean) * rstd
+    dyf = dy.float()
+    dg = dyf * gamma.float()
+    dx = rstd * (dg - dg.mean(-1, keepdim=True) - xh * (dg * xh).mean(-1, keepdim=True))
+    if dgamma is not None:
+        dgamma += (dyf * xh).sum(0)
+    if dbeta is not None:
+        dbeta += dyf.sum(0)
+    if add is not None:
+        dx = dx + add.float()
+    return dx.to(BF).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------- elementwise / glue
+def geglu_fwd(proj):
+    h, g = proj.float().chunk(2, dim=-1)
+    return (h * F.gelu(g)).to(BF).contiguous()
+
+
+@torch.enable_grad()
+def geglu_bwd(proj, dout):
+    p = proj.float().requires_grad_(True)
+    h, g = p.chunk(2, dim=-1)
+    (dp,) = torch.autograd.grad(h * F.gelu(g), p, dout.float())
+    return dp.to(BF).contiguous()
+
+
+def silu_f32_to_bf16(x, apply_silu=True):
+    return (F.silu(x) if apply_silu else x).to(BF)
+
+
+@torch.enable_grad()
+def silu_bwd_f32(x, dy):
+    xx = x.clone().requires_grad_(True)
+    (g,) = torch.autograd.grad(F.silu(xx), xx, dy)
+    return g
+
+
+def silu_bf16(x):
+    return F.silu(x.float()).to(BF)
+
+
+@torch.enable_grad()
+def silu_bf16_bwd(x, dy):
+    xx = x.float().requires_grad_(True)
+    (g,) = torch.autograd.grad(F.silu(xx), xx, dy.float())
+    return g.to(BF)
+
+
+def add_bf16(a, b, c=None):
+    r = a.float() + b.float()
+    if c is not None:
+        r = r + c.float()
+    return r.to(BF)
+
+
+def scale_bf16(a, alpha):
+    return (a.float() * alpha).to(BF)
+
+
+def add_f32(a, b):
+    return a + b
+
+
+def cast_f32_bf16(src, dst=None):
+    if dst is None:
+        return src.to(BF)
+    dst.copy_(src)
+    return dst
+
+
+def upsample_nearest_fwd(x, out_hw_):
+    return F.interpolate(x.float().permute(0, 3, 1, 2), size=tuple(out_hw_), mode="nearest").permute(0, 2, 3, 1).to(BF).contiguous()
+
+
+@torch.enable_grad()
+def upsample_nearest_bwd(dy, in_hw):
+    N, Ho, Wo, C = dy.shape
+    x = torch.zeros((N, C, in_hw[0], in_hw[1]), dtype=torch.float32, device=dy.device, requires_grad=True)
+    y = F.interpolate(x, size=(Ho, Wo), mode="nearest")
+    (g,) = torch.autograd.grad(y, x, dy.float().permute(0, 3, 1, 2))
+    return g.permute(0, 2, 3, 1).to(BF).contiguous()
+
+
+def concat_channels(a, b):
+    return torch.cat([a, b], dim=-1).contiguous()
+
+
+def split_channels(g, Ca):
+    return g[..., :Ca].contiguous(), g[..., Ca:].contiguous()
+
+
+def colsum(x, out, S, P, C):
+    out += x.float().reshape(S, P, C).sum(1)
+
+
+def colsum_f32(x, out):
+    out += x.sum(0)
+
+
+def softmax_fwd(s, n_valid, ld_out):
+    p = torch.softmax(s[..., :n_valid].float(), dim=-1)
+    out = torch.zeros(s.shape[:-1] + (ld_out,), dtype=BF, device=s.device)
+    out[..., :n_valid] = p.to(BF)
+    return out
+
+
+def softmax_bwd(p, dp, n_valid, scale):
+    pf = p.float()[..., :n_valid]
+    d = dp[..., :n_valid]
+    ds = pf * (d - (pf * d).sum(-1, keepdim=True)) * scale
+    out = torch.zeros_like(p)
+    out[..., :n_valid] = ds.to(BF)
+    return out
+
+
+def _seq_view(t, nseq, inner, outer_stride, inner_stride, seq_stride, heads, L, D):
+    return torch.as_strided(t.reshape(-1), (nseq // inner, inner, heads, L, D), (outer_stride, inner_stride, D, seq_stride, 1))
+
+
+def attn_small_fwd(q, k, v, nseq, inner, outer_stride, inner_stride, seq_stride, heads, L, D):
+    args = (nseq, inner, outer_stride, inner_stride, seq_stride, heads, L, D)
+    Q, K, V = (_seq_view(t, *args).float() for t in (q, k, v))
+    P = torch.softmax(Q @ K.transpose(-1, -2) * D ** -0.5, dim=-1)
+    o = torch.empty_like(q)
+    _seq_view(o, *args).copy_((P @ V).to(BF))
+    return o
+
+
+@torch.enable_grad()
+def attn_small_bwd(q, k, v, do, nseq, inner, outer_stride, inner_stride, seq_stride, heads, L, D):
+    args = (nseq, inner, outer_stride, inner_stride, seq_stride, heads, L, D)
+    Q, K, V = (_seq_view(t, *args).float().requires_grad_(True) for t in (q, k, v))
+    O = torch.softmax(Q @ K.transpose(-1, -2) * D ** -0.5, dim=-1) @ V
+    gq, gk, gv = torch.autograd.grad(O, (Q, K, V), _seq_view(do, *args).float())
+    outs = []
+    for g, like in ((gq, q), (gk, k), (gv, v)):
+        o = torch.empty_like(like)
+        _seq_view(o, *args).copy_(g.to(BF))
+        outs.append(o)
+    return tuple(outs)
+
+
+def timestep_embedding(t, dim):
+    half = dim // 2
+    f = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
+    a = t[:, None].float() * f[None]
+    return torch.cat([torch.cos(a), torch.sin(a)], dim=-1).to(BF)
+
+
+def latents_to_nhwc8(x0, noise=None, alphas_cumprod=None, timesteps=None):
+    B, C, Fr, H, W = x0.shape
+    x = x0
+    if noise is not None:
+        a = alphas_cumprod[timesteps].view(B, 1, 1, 1, 1)
+        x = a.sqrt() * x0 + (1 - a).sqrt() * noise
+    out = torch.zeros((B, Fr, H, W, 8), dtype=torch.float32, device=x0.device)
+    out[..., :C] = x.permute(0, 2, 3, 4, 1)
+    return out.view(B * Fr, H, W, 8).to(BF)
+
+
+def nhwc8_to_latents(x, B, C, Fr):
+    _, H, W, _ = x.shape
+    return x.float().view(B, Fr, H, W, 8)[..., :C].permute(0, 4, 1, 2, 3).contiguous()
+
+
+def mse_loss_fwd(pred, target):
+    B, C, Fr, H, W = target.shape
+    p = nhwc8_to_latents(pred, B, C, Fr)
+    return ((p - target) ** 2).mean()
+
+
+def mse_loss_bwd(pred, target, gout):
+    B, C, Fr, H, W = target.shape
+    p = nhwc8_to_latents(pred, B, C, Fr)
+    g = 2.0 * (p - target) / p.numel() * gout
+    return latents_to_nhwc8(g)
+
+
+ALL = [n for n, f in list(globals().items()) if callable(f) and not n.startswith("_") and n not in ("F",)]

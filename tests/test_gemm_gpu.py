@@ -64,14 +64,14 @@ def test_conv_fwd(case):
     res = torch.randn(N, Ho, Wo, Co, device="cuda", generator=g).bfloat16()
     # plain
     y = torch.full((N, Ho, Wo, Co), float("nan"), device="cuda", dtype=torch.bfloat16)
-    epi = nat.Epilogue(None, None, None, 1.0, 0)
+    epi = nat.Epilogue(None, None, None, 1.0, 0, 1)
     nat.check(nat.lib().t2v_conv_fwd(P(x), P(w), P(y), N, H, W, Ci, Co, KH, KW, s, *pads, ctypes.byref(epi), stream()))
     torch.cuda.synchronize()
     e = rel_err(y, ref)
     assert e < 1e-2, f"plain conv rel err {e}"
     # fused epilogue, fp32 output
     y2 = torch.full((N, Ho, Wo, Co), float("nan"), device="cuda", dtype=torch.float32)
-    epi = nat.Epilogue(bias.data_ptr(), rowbias.data_ptr(), res.data_ptr(), 0.5, 1)
+    epi = nat.Epilogue(bias.data_ptr(), rowbias.data_ptr(), res.data_ptr(), 0.5, 1, 1)
     nat.check(nat.lib().t2v_conv_fwd(P(x), P(w), P(y2), N, H, W, Ci, Co, KH, KW, s, *pads, ctypes.byref(epi), stream()))
     torch.cuda.synchronize()
     ref2 = 0.5 * ref + bias + rowbias[:, None, None, :] + res.float()
@@ -98,7 +98,7 @@ def test_conv_dgrad_wgrad(case):
     # dgrad (+ residual add)
     other = torch.randn(N, H, W, Ci, device="cuda", generator=g).bfloat16()
     dx = torch.full((N, H, W, Ci), float("nan"), device="cuda", dtype=torch.bfloat16)
-    epi = nat.Epilogue(None, None, other.data_ptr(), 1.0, 0)
+    epi = nat.Epilogue(None, None, other.data_ptr(), 1.0, 0, 1)
     nat.check(nat.lib().t2v_conv_dgrad(P(dy), P(w), P(dx), N, H, W, Ci, Co, KH, KW, s, *pads, ctypes.byref(epi), stream()))
     torch.cuda.synchronize()
     e = rel_err(dx, xf.grad + other.float())

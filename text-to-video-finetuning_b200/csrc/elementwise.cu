@@ -1,0 +1,485 @@
+// HBM-bound glue kernels of the finetune step: layout conversion at the latent boundary (fused with add_noise / MSE),
+// GEGLU, SiLU, nearest up-sampling, channel concat/split, bias gradients, softmax, casts.
+// All use 128-bit accesses on channels-last bf16 data and grid-stride loops sized in multiples of the SM count.
+#include "common.h"
+#include "ptx.cuh"
+
+#include <algorithm>
+#include <cuda_bf16.h>
+
+namespace t2v {
+
+__device__ __forceinline__ void unpack8e(const uint4& q, float* v) {
+    v[0] = bf16_lo(q.x); v[1] = bf16_hi(q.x); v[2] = bf16_lo(q.y); v[3] = bf16_hi(q.y);
+    v[4] = bf16_lo(q.z); v[5] = bf16_hi(q.z); v[6] = bf16_lo(q.w); v[7] = bf16_hi(q.w);
+}
+__device__ __forceinline__ uint4 pack8e(const float* v) {
+    uint4 q;
+    q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]); q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
+    return q;
+}
+__device__ __forceinline__ float sigm(float z) { return 1.0f / (1.0f + __expf(-z)); }
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+    return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.39894228040143268f * __expf(-0.5f * x * x);
+}
+
+static inline int ew_grid(int64_t n, int threads = 256) {
+    return int(std::min<int64_t>((n + threads - 1) / threads, 148 * 16));
+}
+#define GRID_STRIDE(i, n) for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < (n); i += int64_t(gridDim.x) * blockDim.x)
+
+// ------------------------------------------------------------------------------------------------ latent boundary
+// (B, C<=8, F, H, W) fp32  ->  [B*F][H][W][8] bf16 (zero-padded channels), optionally fused with DDPM add_noise:
+//   x_t = sqrt(abar[t_b]) x0 + sqrt(1 - abar[t_b]) eps        (train.py:760)
+__global__ void to_nhwc8_kernel(const float* __restrict__ x0, const float* __restrict__ noise, const float* __restrict__ abar,
+                                const int64_t* __restrict__ t, __nv_bfloat16* __restrict__ out, int B, int C, int F, int HW) {
+    const int64_t npix = int64_t(B) * F * HW;
+    GRID_STRIDE(i, npix) {
+        const int hw = int(i % HW);
+        const int f = int((i / HW) % F);
+        const int b = int(i / (int64_t(HW) * F));
+        float sa = 1.f, sb = 0.f;
+        if (noise) {
+            const float a = abar[t[b]];
+            sa = sqrtf(a);
+            sb = sqrtf(1.f - a);
+        }
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float x = 0.f;
+            if (c < C) {
+                const int64_t src = ((int64_t(b) * C + c) * F + f) * HW + hw;
+                x = sa * x0[src];
+                if (noise) x += sb * noise[src];
+            }
+            v[c] = x;
+        }
+        reinterpret_cast<uint4*>(out)[i] = pack8e(v);
+    }
+}
+
+// [B*F][H][W][8] bf16 -> (B, C, F, H, W) fp32
+__global__ void from_nhwc8_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int B, int C, int F, int HW) {
+    const int64_t npix = int64_t(B) * F * HW;
+    GRID_STRIDE(i, npix) {
+        const int hw = int(i % HW);
+        const int f = int((i / HW) % F);
+        const int b = int(i / (int64_t(HW) * F));
+        float v[8];
+        unpack8e(__ldg(reinterpret_cast<const uint4*>(in) + i), v);
+        for (int c = 0; c < C; ++c) out[((int64_t(b) * C + c) * F + f) * HW + hw] = v[c];
+    }
+}
+
+// (B, C, F, H, W) fp32 gradient -> [B*F][H][W][8] bf16 scaled by *gscale (device scalar or NULL)
+// MSE forward: loss += sum (pred - target)^2 / numel ; backward: dpred = g * 2 (pred - target) / numel
+__global__ void mse_kernel(const __nv_bfloat16* __restrict__ pred, const float* __restrict__ target, float* __restrict__ loss,
+                           const float* __restrict__ gout, __nv_bfloat16* __restrict__ dpred, int B, int C, int F, int HW) {
+    const int64_t npix = int64_t(B) * F * HW;
+    const float inv = 1.0f / (float(npix) * C);
+    const float g = (dpred && gout) ? *gout : 1.0f;
+    float acc = 0.f;
+    GRID_STRIDE(i, npix) {
+        const int hw = int(i % HW);
+        const int f = int((i / HW) % F);
+        const int b = int(i / (int64_t(HW) * F));
+        float v[8], d[8];
+        unpack8e(__ldg(reinterpret_cast<const uint4*>(pred) + i), v);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float e = 0.f;
+            if (c < C) e = v[c] - target[((int64_t(b) * C + c) * F + f) * HW + hw];
+            acc += e * e;
+            d[c] = 2.f * e * inv * g;
+        }
+        if (dpred) reinterpret_cast<uint4*>(dpred)[i] = pack8e(d);
+    }
+    if (loss) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        __shared__ float ws[32];
+        if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float a = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (threadIdx.x == 0) atomicAdd(loss, a * inv);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ activations
+// GEGLU: proj [M][2I] -> out [M][I] = h * gelu(gate)   (diffusers GEGLU; exact erf GELU)
+__global__ void geglu_fwd_kernel(const __nv_bfloat16* __restrict__ proj, __nv_bfloat16* __restrict__ out, int64_t M, int I) {
+    const int V = I >> 3;
+    GRID_STRIDE(i, M * V) {
+        const int64_t m = i / V;
+        const int cv = int(i % V);
+        float h[8], g[8];
+        const uint4* row = reinterpret_cast<const uint4*>(proj + m * 2 * I);
+        unpack8e(__ldg(row + cv), h);
+        unpack8e(__ldg(row + V + cv), g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[j] *= gelu_erf(g[j]);
+        reinterpret_cast<uint4*>(out)[i] = pack8e(h);
+    }
+}
+__global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ proj, const __nv_bfloat16* __restrict__ dout,
+                                 __nv_bfloat16* __restrict__ dproj, int64_t M, int I) {
+    const int V = I >> 3;
+    GRID_STRIDE(i, M * V) {
+        const int64_t m = i / V;
+        const int cv = int(i % V);
+        float h[8], g[8], d[8], dh[8], dg[8];
+        const uint4* row = reinterpret_cast<const uint4*>(proj + m * 2 * I);
+        unpack8e(__ldg(row + cv), h);
+        unpack8e(__ldg(row + V + cv), g);
+        unpack8e(__ldg(reinterpret_cast<const uint4*>(dout) + i), d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            dh[j] = d[j] * gelu_erf(g[j]);
+            dg[j] = d[j] * h[j] * gelu_erf_grad(g[j]);
+        }
+        uint4* orow = reinterpret_cast<uint4*>(dproj + m * 2 * I);
+        orow[cv] = pack8e(dh);
+        orow[V + cv] = pack8e(dg);
+    }
+}
+
+// SiLU on a small fp32 tensor (time embedding path): y_bf16 = silu(x_f32);  backward: dx_f32 = dy_f32 * silu'(x)
+__global__ void silu_f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n, int apply) {
+    GRID_STRIDE(i, n) {
+        const float v = x[i];
+        y[i] = __float2bfloat16_rn(apply ? v * sigm(v) : v);
+    }
+}
+__global__ void silu_bwd_f32_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int64_t n,
+                                    int accumulate) {
+    GRID_STRIDE(i, n) {
+        const float v = x[i], s = sigm(v);
+        const float g = dy[i] * s * (1.f + v * (1.f - s));
+        dx[i] = accumulate ? dx[i] + g : g;
+    }
+}
+
+__global__ void silu_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
+    GRID_STRIDE(i, n) {
+        const float v = __bfloat162float(x[i]);
+        y[i] = __float2bfloat16_rn(v * sigm(v));
+    }
+}
+__global__ void silu_bf16_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                     __nv_bfloat16* __restrict__ dx, int64_t n) {
+    GRID_STRIDE(i, n) {
+        const float v = __bfloat162float(x[i]), s = sigm(v);
+        dx[i] = __float2bfloat16_rn(__bfloat162float(dy[i]) * s * (1.f + v * (1.f - s)));
+    }
+}
+
+// out = a + b (+ c)   (gradient fan-in)
+__global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                           const __nv_bfloat16* __restrict__ c, __nv_bfloat16* __restrict__ out, int64_t nvec) {
+    GRID_STRIDE(i, nvec) {
+        float x[8], y[8];
+        unpack8e(__ldg(reinterpret_cast<const uint4*>(a) + i), x);
+        unpack8e(__ldg(reinterpret_cast<const uint4*>(b) + i), y);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] += y[j];
+        if (c) {
+            unpack8e(__ldg(reinterpret_cast<const uint4*>(c) + i), y);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] += y[j];
+        }
+        reinterpret_cast<uint4*>(out)[i] = pack8e(x);
+    }
+}
+__global__ void scale_bf16_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ out, int64_t nvec, float alpha) {
+    GRID_STRIDE(i, nvec) {
+        float x[8];
+        unpack8e(__ldg(reinterpret_cast<const uint4*>(a) + i), x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] *= alpha;
+        reinterpret_cast<uint4*>(out)[i] = pack8e(x);
+    }
+}
+__global__ void add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t n) {
+    GRID_STRIDE(i, n) out[i] = a[i] + b[i];
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+    const int64_t nv = n >> 3;
+    GRID_STRIDE(i, nv) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        reinterpret_cast<uint4*>(dst)[i] = pack8e(v);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 7)) dst[(nv << 3) + threadIdx.x] = __float2bfloat16_rn(src[(nv << 3) + threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------------ resampling / concat
+// nearest-neighbour resize [N][H][W][C] -> [N][Ho][Wo][C]  (src = floor(dst * in / out), F.interpolate 'nearest')
+__global__ void upsample_nearest_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
+                                            int W, int Ho, int Wo, int C) {
+    const int V = C >> 3;
+    const int64_t total = int64_t(N) * Ho * Wo * V;
+    GRID_STRIDE(i, total) {
+        const int cv = int(i % V);
+        int64_t r = i / V;
+        const int wo = int(r % Wo);
+        r /= Wo;
+        const int ho = int(r % Ho);
+        const int n = int(r / Ho);
+        const int hi = min(H - 1, int(int64_t(ho) * H / Ho)), wi = min(W - 1, int(int64_t(wo) * W / Wo));
+        reinterpret_cast<uint4*>(y)[i] = __ldg(reinterpret_cast<const uint4*>(x) + ((int64_t(n) * H + hi) * W + wi) * V + cv);
+    }
+}
+// backward of the nearest resize: dx[h][w] = sum of dy over the output pixels that read (h, w)
+__global__ void upsample_nearest_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int N, int H,
+                                            int W, int Ho, int Wo, int C) {
+    const int V = C >> 3;
+    const int64_t total = int64_t(N) * H * W * V;
+    GRID_STRIDE(i, total) {
+        const int cv = int(i % V);
+        int64_t r = i / V;
+        const int w = int(r % W);
+        r /= W;
+        const int h = int(r % H);
+        const int n = int(r / H);
+        // floor(ho * H / Ho) == h  <=>  ceil(h Ho / H) <= ho < ceil((h+1) Ho / H)
+        const int ho0 = int((int64_t(h) * Ho + H - 1) / H), ho1 = int((int64_t(h + 1) * Ho + H - 1) / H);
+        const int wo0 = int((int64_t(w) * Wo + W - 1) / W), wo1 = int((int64_t(w + 1) * Wo + W - 1) / W);
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int a = ho0; a < ho1; ++a)
+            for (int b = wo0; b < wo1; ++b) {
+                float v[8];
+                unpack8e(__ldg(reinterpret_cast<const uint4*>(dy) + ((int64_t(n) * Ho + a) * Wo + b) * V + cv), v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += v[j];
+            }
+        reinterpret_cast<uint4*>(dx)[i] = pack8e(acc);
+    }
+}
+
+// strided 2-D copy of bf16 rows: dst[m][dst_off + c] = src[m][src_off + c], c < C  (concat / split of channels)
+__global__ void copy_cols_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t M, int C,
+                                 int src_ld, int src_off, int dst_ld, int dst_off) {
+    const int V = C >> 3;
+    GRID_STRIDE(i, M * V) {
+        const int64_t m = i / V;
+        const int cv = int(i % V);
+        *reinterpret_cast<uint4*>(dst + m * dst_ld + dst_off + cv * 8) =
+            __ldg(reinterpret_cast<const uint4*>(src + m * src_ld + src_off + cv * 8));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ reductions
+// Segmented column sum: out[s][c] (+)= sum_p x[s][p][c].  Grid (chunks, S); per-thread 8-channel vectors.
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int64_t P, int C, int chunk_rows) {
+    extern __shared__ float sh[];  // [C]
+    const int s = blockIdx.y;
+    const int V = C >> 3;
+    const int lanes = blockDim.x / V;
+    const int cv = threadIdx.x % V, pl = threadIdx.x / V;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+    if (pl < lanes) {
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const int64_t p0 = int64_t(blockIdx.x) * chunk_rows, p1 = min(P, p0 + chunk_rows);
+        const uint4* xs = reinterpret_cast<const uint4*>(x + int64_t(s) * P * C) + cv;
+        for (int64_t p = p0 + pl; p < p1; p += lanes) {
+            float v[8];
+            unpack8e(__ldg(xs + p * V), v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += v[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&sh[cv * 8 + j], acc[j]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(out + int64_t(s) * C + c, sh[c]);
+}
+// out[c] += sum_s x[s][c] for a small fp32 matrix
+__global__ void colsum_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int S, int C) {
+    GRID_STRIDE(c, C) {
+        float a = 0.f;
+        for (int s = 0; s < S; ++s) a += x[int64_t(s) * C + c];
+        out[c] += a;
+    }
+}
+
+// Row softmax over fp32 scores -> bf16 probabilities; columns >= n_valid (padding up to ld_out) are written as 0.
+__global__ void softmax_fwd_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, int64_t rows, int n_valid, int ld_in,
+                                   int ld_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+    const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        const float* sr = s + r * ld_in;
+        float mx = -INFINITY;
+        for (int c = lane; c < n_valid; c += 32) mx = fmaxf(mx, sr[c]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+        for (int c = lane; c < n_valid; c += 32) sum += __expf(sr[c] - mx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float inv = 1.f / sum;
+        __nv_bfloat16* pr = p + r * ld_out;
+        for (int c = lane; c < ld_out; c += 32) pr[c] = __float2bfloat16_rn(c < n_valid ? __expf(sr[c] - mx) * inv : 0.f);
+    }
+}
+// dS = P * (dP - rowsum(dP * P)) * scale  -> bf16 (padding columns zero)
+__global__ void softmax_bwd_kernel(const __nv_bfloat16* __restrict__ p, const float* __restrict__ dp, __nv_bfloat16* __restrict__ ds,
+                                   int64_t rows, int n_valid, int ld_p, int ld_dp, float scale) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+    const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        const __nv_bfloat16* pr = p + r * ld_p;
+        const float* dr = dp + r * ld_dp;
+        float dot = 0.f;
+        for (int c = lane; c < n_valid; c += 32) dot += __bfloat162float(pr[c]) * dr[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        __nv_bfloat16* o_ = ds + r * ld_p;
+        for (int c = lane; c < ld_p; c += 32)
+            o_[c] = __float2bfloat16_rn(c < n_valid ? __bfloat162float(pr[c]) * (dr[c] - dot) * scale : 0.f);
+    }
+}
+
+// Timesteps(dim, flip_sin_to_cos=True, shift=0): [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(10000) i / half)  -> bf16 [B][dim]
+__global__ void timestep_embed_kernel(const int64_t* __restrict__ t, __nv_bfloat16* __restrict__ out, int B, int dim) {
+    const int half = dim >> 1;
+    GRID_STRIDE(i, int64_t(B) * half) {
+        const int b = int(i / half), k = int(i % half);
+        const float f = expf(-9.210340371976184f * float(k) / float(half));
+        const float a = float(t[b]) * f;
+        out[int64_t(b) * dim + k] = __float2bfloat16_rn(cosf(a));
+        out[int64_t(b) * dim + half + k] = __float2bfloat16_rn(sinf(a));
+    }
+}
+
+}  // namespace t2v
+
+using namespace t2v;
+#define ST static_cast<cudaStream_t>(stream)
+#define BF(p) static_cast<const __nv_bfloat16*>(p)
+#define BFW(p) static_cast<__nv_bfloat16*>(p)
+
+extern "C" {
+
+int t2v_latents_to_nhwc8(const float* x0, const float* noise, const float* alphas_cumprod, const int64_t* timesteps, void* out,
+                         int32_t B, int32_t C, int32_t F, int32_t HW, void* stream) {
+    if (C > 8) return fail(-2, "latents_to_nhwc8: C=%d > 8", C);
+    const int64_t n = int64_t(B) * F * HW;
+    to_nhwc8_kernel<<<ew_grid(n), 256, 0, ST>>>(x0, noise, alphas_cumprod, timesteps, BFW(out), B, C, F, HW);
+    return launch_checked(int(cudaGetLastError()), "latents_to_nhwc8");
+}
+int t2v_nhwc8_to_latents(const void* in, float* out, int32_t B, int32_t C, int32_t F, int32_t HW, void* stream) {
+    const int64_t n = int64_t(B) * F * HW;
+    from_nhwc8_kernel<<<ew_grid(n), 256, 0, ST>>>(BF(in), out, B, C, F, HW);
+    return launch_checked(int(cudaGetLastError()), "nhwc8_to_latents");
+}
+int t2v_mse_loss(const void* pred, const float* target, float* loss, const float* gout, void* dpred, int32_t B, int32_t C,
+                 int32_t F, int32_t HW, void* stream) {
+    const int64_t n = int64_t(B) * F * HW;
+    if (loss) cudaMemsetAsync(loss, 0, sizeof(float), ST);
+    mse_kernel<<<ew_grid(n), 256, 0, ST>>>(BF(pred), target, loss, gout, BFW(dpred), B, C, F, HW);
+    return launch_checked(int(cudaGetLastError()), "mse_loss");
+}
+int t2v_geglu_fwd(const void* proj, void* out, int64_t M, int32_t I, void* stream) {
+    if (I % 8) return fail(-2, "geglu: inner dim %d not a multiple of 8", I);
+    geglu_fwd_kernel<<<ew_grid(M * (I / 8)), 256, 0, ST>>>(BF(proj), BFW(out), M, I);
+    return launch_checked(int(cudaGetLastError()), "geglu_fwd");
+}
+int t2v_geglu_bwd(const void* proj, const void* dout, void* dproj, int64_t M, int32_t I, void* stream) {
+    if (I % 8) return fail(-2, "geglu: inner dim %d not a multiple of 8", I);
+    geglu_bwd_kernel<<<ew_grid(M * (I / 8)), 256, 0, ST>>>(BF(proj), BF(dout), BFW(dproj), M, I);
+    return launch_checked(int(cudaGetLastError()), "geglu_bwd");
+}
+int t2v_silu_f32_to_bf16(const float* x, void* y, int64_t n, int32_t apply_silu, void* stream) {
+    silu_f32_to_bf16_kernel<<<ew_grid(n), 256, 0, ST>>>(x, BFW(y), n, apply_silu);
+    return launch_checked(int(cudaGetLastError()), "silu_f32_to_bf16");
+}
+int t2v_silu_bwd_f32(const float* x, const float* dy, float* dx, int64_t n, int32_t accumulate, void* stream) {
+    silu_bwd_f32_kernel<<<ew_grid(n), 256, 0, ST>>>(x, dy, dx, n, accumulate);
+    return launch_checked(int(cudaGetLastError()), "silu_bwd_f32");
+}
+int t2v_silu_bf16(const void* x, void* y, int64_t n, void* stream) {
+    silu_bf16_kernel<<<ew_grid(n), 256, 0, ST>>>(BF(x), BFW(y), n);
+    return launch_checked(int(cudaGetLastError()), "silu_bf16");
+}
+int t2v_silu_bf16_bwd(const void* x, const void* dy, void* dx, int64_t n, void* stream) {
+    silu_bf16_bwd_kernel<<<ew_grid(n), 256, 0, ST>>>(BF(x), BF(dy), BFW(dx), n);
+    return launch_checked(int(cudaGetLastError()), "silu_bf16_bwd");
+}
+int t2v_add_bf16(const void* a, const void* b, const void* c, void* out, int64_t n, void* stream) {
+    if (n % 8) return fail(-2, "add_bf16: n must be a multiple of 8");
+    add_kernel<<<ew_grid(n / 8), 256, 0, ST>>>(BF(a), BF(b), BF(c), BFW(out), n / 8);
+    return launch_checked(int(cudaGetLastError()), "add_bf16");
+}
+int t2v_scale_bf16(const void* a, void* out, int64_t n, float alpha, void* stream) {
+    if (n % 8) return fail(-2, "scale_bf16: n must be a multiple of 8");
+    scale_bf16_kernel<<<ew_grid(n / 8), 256, 0, ST>>>(BF(a), BFW(out), n / 8, alpha);
+    return launch_checked(int(cudaGetLastError()), "scale_bf16");
+}
+int t2v_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream) {
+    add_f32_kernel<<<ew_grid(n), 256, 0, ST>>>(a, b, out, n);
+    return launch_checked(int(cudaGetLastError()), "add_f32");
+}
+int t2v_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
+    cast_f32_bf16_kernel<<<ew_grid(std::max<int64_t>(n / 8, 1)), 256, 0, ST>>>(src, BFW(dst), n);
+    return launch_checked(int(cudaGetLastError()), "cast_f32_bf16");
+}
+int t2v_upsample_nearest_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t Ho, int32_t Wo, int32_t C, void* stream) {
+    if (C % 8) return fail(-2, "upsample: C %% 8 != 0");
+    upsample_nearest_fwd_kernel<<<ew_grid(int64_t(N) * Ho * Wo * (C / 8)), 256, 0, ST>>>(BF(x), BFW(y), N, H, W, Ho, Wo, C);
+    return launch_checked(int(cudaGetLastError()), "upsample_nearest_fwd");
+}
+int t2v_upsample_nearest_bwd(const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t Ho, int32_t Wo, int32_t C, void* stream) {
+    if (C % 8) return fail(-2, "upsample: C %% 8 != 0");
+    upsample_nearest_bwd_kernel<<<ew_grid(int64_t(N) * H * W * (C / 8)), 256, 0, ST>>>(BF(dy), BFW(dx), N, H, W, Ho, Wo, C);
+    return launch_checked(int(cudaGetLastError()), "upsample_nearest_bwd");
+}
+int t2v_copy_cols(const void* src, void* dst, int64_t M, int32_t C, int32_t src_ld, int32_t src_off, int32_t dst_ld, int32_t dst_off,
+                  void* stream) {
+    if (C % 8 || src_ld % 8 || src_off % 8 || dst_ld % 8 || dst_off % 8) return fail(-2, "copy_cols: all extents must be multiples of 8");
+    copy_cols_kernel<<<ew_grid(M * (C / 8)), 256, 0, ST>>>(BF(src), BFW(dst), M, C, src_ld, src_off, dst_ld, dst_off);
+    return launch_checked(int(cudaGetLastError()), "copy_cols");
+}
+int t2v_colsum(const void* x, float* out, int32_t S, int64_t P, int32_t C, void* stream) {
+    if (C % 8 || C / 8 > 1024) return fail(-2, "colsum: C=%d unsupported", C);
+    const int V = C / 8;
+    int bs = 256;
+    while (bs < V) bs += 32;
+    const int64_t want = std::max<int64_t>(1, (4 * 148 + S - 1) / S);
+    const int chunk = int(std::min<int64_t>(P, std::max<int64_t>(16, (P + want - 1) / want)));
+    const int chunks = int((P + chunk - 1) / chunk);
+    colsum_kernel<<<dim3(chunks, S), bs, C * sizeof(float), ST>>>(BF(x), out, P, C, chunk);
+    return launch_checked(int(cudaGetLastError()), "colsum");
+}
+int t2v_colsum_f32(const float* x, float* out, int32_t S, int32_t C, void* stream) {
+    colsum_f32_kernel<<<ew_grid(C), 256, 0, ST>>>(x, out, S, C);
+    return launch_checked(int(cudaGetLastError()), "colsum_f32");
+}
+int t2v_softmax_fwd(const float* s, void* p, int64_t rows, int32_t n_valid, int32_t ld_in, int32_t ld_out, void* stream) {
+    const int grid = int(std::min<int64_t>((rows + 7) / 8, 148 * 16));
+    softmax_fwd_kernel<<<grid, 256, 0, ST>>>(s, BFW(p), rows, n_valid, ld_in, ld_out);
+    return launch_checked(int(cudaGetLastError()), "softmax_fwd");
+}
+int t2v_softmax_bwd(const void* p, const float* dp, void* ds, int64_t rows, int32_t n_valid, int32_t ld_p, int32_t ld_dp, float scale,
+                    void* stream) {
+    const int grid = int(std::min<int64_t>((rows + 7) / 8, 148 * 16));
+    softmax_bwd_kernel<<<grid, 256, 0, ST>>>(BF(p), dp, BFW(ds), rows, n_valid, ld_p, ld_dp, scale);
+    return launch_checked(int(cudaGetLastError()), "softmax_bwd");
+}
+int t2v_timestep_embedding(const int64_t* t, void* out, int32_t B, int32_t dim, void* stream) {
+    timestep_embed_kernel<<<ew_grid(int64_t(B) * dim / 2), 256, 0, ST>>>(t, BFW(out), B, dim);
+    return launch_checked(int(cudaGetLastError()), "timestep_embedding");
+}
+
+}  // extern "C"

@@ -74,6 +74,7 @@ void fill_epilogue(GemmParams& p, const T2VEpilogue* e, void* out, int out_mode_
     p.rowbias = e ? e->rowbias : nullptr;
     p.residual = e ? e->residual : nullptr;
     p.out_mode = e ? (e->out_fp32 ? OUT_F32 : OUT_BF16) : out_mode_default;
+    p.rb_div = (e && e->rowbias_div > 0) ? e->rowbias_div : 1;
     p.flags = 0;
     if (p.bias) p.flags |= EPI_BIAS;
     if (p.rowbias) p.flags |= EPI_ROWBIAS;
@@ -212,7 +213,7 @@ int t2v_conv_dgrad(const void* dy, const void* w, void* dx, int32_t N, int32_t H
             p.ldw = int64_t(s) * Cin; p.ldh = int64_t(s) * W * Cin; p.ldn = int64_t(H) * W * Cin;
             p.rb_ld = Cin;
             const int64_t base_off = (int64_t(ph) * W + pw) * Cin;
-            T2VEpilogue e = epi ? *epi : T2VEpilogue{nullptr, nullptr, nullptr, 1.0f, 0};
+            T2VEpilogue e = epi ? *epi : T2VEpilogue{nullptr, nullptr, nullptr, 1.0f, 0, 1};
             const size_t esz = e.out_fp32 ? 4 : 2;
             fill_epilogue(p, &e, static_cast<char*>(dx) + base_off * esz, OUT_BF16);
             if (p.residual) p.residual = static_cast<const char*>(p.residual) + base_off * 2;
@@ -341,7 +342,7 @@ int t2v_bgemm(const T2VMat* A, const T2VMat* B, void* C, int64_t ldc, int64_t c_
     p.W = M; p.H = splits; p.N = 1; p.ncols = N;
     p.ldw = ldc; p.ldh = 0; p.ldn = 0;
     p.otc[4] = c_stride_z2; p.otc[5] = c_stride_z1;
-    T2VEpilogue e{nullptr, nullptr, nullptr, alpha, out_mode != OUT_BF16};
+    T2VEpilogue e{nullptr, nullptr, nullptr, alpha, out_mode != OUT_BF16, 1};
     fill_epilogue(p, &e, C, OUT_BF16);
     p.out_mode = out_mode;
     set_vec_flag(p);

@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                         }
                     }
                     if (has_rb) {
-                        const float4* b4 = reinterpret_cast<const float4*>(p.rowbias + gn * p.rb_ld + col);
+                        const float4* b4 = reinterpret_cast<const float4*>(p.rowbias + (gn / p.rb_div) * p.rb_ld + col);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float4 b = __ldg(b4 + j);
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                         if (col + j >= p.ncols) break;
                         float x = v[j];
                         if (has_bias) x += p.bias[col + j];
-                        if (has_rb) x += p.rowbias[gn * p.rb_ld + col + j];
+                        if (has_rb) x += p.rowbias[(gn / p.rb_div) * p.rb_ld + col + j];
                         if (has_res) x += __bfloat162float(static_cast<const __nv_bfloat16*>(p.residual)[off + col + j]);
                         if (p.out_mode == OUT_BF16) static_cast<__nv_bfloat16*>(p.out)[off + col + j] = __float2bfloat16_rn(x);
                         else if (p.out_mode == OUT_F32) static_cast<float*>(p.out)[off + col + j] = x;

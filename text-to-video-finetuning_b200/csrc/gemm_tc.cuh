@@ -69,6 +69,8 @@ struct alignas(64) GemmParams {
     int64_t ldw, ldh, ldn; // element strides of the row-space coordinates in the output
     int64_t otc[6];        // extra element offset per tile variable
     int64_t rb_ld;
+    int32_t rb_div;
+    int32_t pad2_;
     void* out;
     const void* residual;
     const float* bias;

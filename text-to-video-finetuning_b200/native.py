@@ -13,7 +13,7 @@ LIB_DIR = os.path.join(_HERE, "_native")
 LIB_PATH = os.path.join(LIB_DIR, "libt2v_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "--use_fast_math", "-shared",
+    "-Xcompiler", "-fPIC", "-shared",
 ]
 
 _lib = None
@@ -51,12 +51,22 @@ def build(force=False, verbose=False):
 
 class Epilogue(ctypes.Structure):
     _fields_ = [("bias", ctypes.c_void_p), ("rowbias", ctypes.c_void_p), ("residual", ctypes.c_void_p),
-                ("alpha", ctypes.c_float), ("out_fp32", ctypes.c_int32)]
+                ("alpha", ctypes.c_float), ("out_fp32", ctypes.c_int32), ("rowbias_div", ctypes.c_int32)]
 
 
 class Mat(ctypes.Structure):
     _fields_ = [("ptr", ctypes.c_void_p), ("ld", ctypes.c_int64), ("stride_z1", ctypes.c_int64),
                 ("stride_z2", ctypes.c_int64), ("kmajor", ctypes.c_int32)]
+
+
+EXPORTS = [
+    "t2v_version", "t2v_last_error", "t2v_launch_count", "t2v_conv_fwd", "t2v_conv_dgrad", "t2v_conv_wgrad", "t2v_bgemm",
+    "t2v_groupnorm_workspace_bytes", "t2v_groupnorm_fwd", "t2v_groupnorm_bwd", "t2v_layernorm_fwd", "t2v_layernorm_bwd",
+    "t2v_latents_to_nhwc8", "t2v_nhwc8_to_latents", "t2v_mse_loss", "t2v_geglu_fwd", "t2v_geglu_bwd", "t2v_silu_f32_to_bf16",
+    "t2v_silu_bwd_f32", "t2v_silu_bf16", "t2v_silu_bf16_bwd", "t2v_add_bf16", "t2v_add_f32", "t2v_scale_bf16", "t2v_cast_f32_bf16", "t2v_upsample_nearest_fwd",
+    "t2v_upsample_nearest_bwd", "t2v_copy_cols", "t2v_colsum", "t2v_colsum_f32", "t2v_softmax_fwd", "t2v_softmax_bwd",
+    "t2v_timestep_embedding", "t2v_attn_small_fwd", "t2v_attn_small_bwd",
+]
 
 
 def _declare(lib):
@@ -69,8 +79,37 @@ def _declare(lib):
     lib.t2v_conv_dgrad.argtypes = conv_args + [ctypes.POINTER(Epilogue), vp]
     lib.t2v_conv_wgrad.argtypes = conv_args + [vp]
     lib.t2v_bgemm.argtypes = [ctypes.POINTER(Mat), ctypes.POINTER(Mat), vp, i64, i64, i64, i32, i32, i32, i32, i32, f32, i32, vp]
-    for name in dir(lib):
-        pass
+    lib.t2v_groupnorm_workspace_bytes.restype = i64
+    lib.t2v_groupnorm_workspace_bytes.argtypes = [i32, i64, i32]
+    lib.t2v_groupnorm_fwd.argtypes = [vp] * 7 + [i32, i64, i32, i32, f32, i32, vp]
+    lib.t2v_groupnorm_bwd.argtypes = [vp] * 10 + [i32, i64, i32, i32, i32, vp]
+    lib.t2v_layernorm_fwd.argtypes = [vp] * 5 + [i64, i32, f32, vp]
+    lib.t2v_layernorm_bwd.argtypes = [vp] * 8 + [i64, i32, vp]
+    lib.t2v_latents_to_nhwc8.argtypes = [vp] * 5 + [i32] * 4 + [vp]
+    lib.t2v_nhwc8_to_latents.argtypes = [vp, vp] + [i32] * 4 + [vp]
+    lib.t2v_mse_loss.argtypes = [vp] * 5 + [i32] * 4 + [vp]
+    lib.t2v_geglu_fwd.argtypes = [vp, vp, i64, i32, vp]
+    lib.t2v_geglu_bwd.argtypes = [vp, vp, vp, i64, i32, vp]
+    lib.t2v_silu_f32_to_bf16.argtypes = [vp, vp, i64, i32, vp]
+    lib.t2v_silu_bwd_f32.argtypes = [vp, vp, vp, i64, i32, vp]
+    lib.t2v_silu_bf16.argtypes = [vp, vp, i64, vp]
+    lib.t2v_silu_bf16_bwd.argtypes = [vp, vp, vp, i64, vp]
+    lib.t2v_add_bf16.argtypes = [vp, vp, vp, vp, i64, vp]
+    lib.t2v_scale_bf16.argtypes = [vp, vp, i64, f32, vp]
+    lib.t2v_add_f32.argtypes = [vp, vp, vp, i64, vp]
+    lib.t2v_cast_f32_bf16.argtypes = [vp, vp, i64, vp]
+    lib.t2v_upsample_nearest_fwd.argtypes = [vp, vp] + [i32] * 6 + [vp]
+    lib.t2v_upsample_nearest_bwd.argtypes = [vp, vp] + [i32] * 6 + [vp]
+    lib.t2v_copy_cols.argtypes = [vp, vp, i64] + [i32] * 5 + [vp]
+    lib.t2v_colsum.argtypes = [vp, vp, i32, i64, i32, vp]
+    lib.t2v_colsum_f32.argtypes = [vp, vp, i32, i32, vp]
+    lib.t2v_softmax_fwd.argtypes = [vp, vp, i64, i32, i32, i32, vp]
+    lib.t2v_softmax_bwd.argtypes = [vp, vp, vp, i64, i32, i32, i32, f32, vp]
+    lib.t2v_timestep_embedding.argtypes = [vp, vp, i32, i32, vp]
+    lib.t2v_attn_small_fwd.argtypes = [vp] * 4 + [i64, i32, i64, i64, i64, i32, i32, i32, vp]
+    lib.t2v_attn_small_bwd.argtypes = [vp] * 7 + [i64, i32, i64, i64, i64, i32, i32, i32, vp]
+    for name in EXPORTS:
+        getattr(lib, name)  # every declared symbol must be exported
     return lib
 
 

@@ -1,0 +1,408 @@
+"""Autograd layer of the hot path: every differentiable op is a torch.autograd.Function whose forward and backward
+call the sm_100a kernels through prims.py.  PyTorch is used for tensor lifetime, streams and the autograd tape only.
+
+Conventions
+  * activations: bf16, channels-last; a frame batch is a 4-D tensor [N, H, W, C], a token matrix is [rows, C]
+  * parameters stay fp32 `nn.Parameter`s with the diffusers names/shapes.  Conv weights are kept in torch
+    channels_last memory format so that their storage *is* the [Cout, KH, KW, Cin] layout the kernels consume.
+  * parameter gradients are accumulated by the kernels straight into `param.grad` (fp32, same physical layout);
+    the Functions return None for them.  This is what lets the data-parallel step all-reduce one flat buffer.
+  * fan-out of an activation is made explicit with `fork`, so gradient fan-in runs in our add kernel.
+"""
+import torch
+from torch.autograd import Function
+
+from . import prims
+
+# ---------------------------------------------------------------------------------------------------- parameters
+
+
+def _phys(p):
+    """The contiguous physical view of a weight: [Cout, KH, KW, Cin] for conv weights, [out, in] for linear."""
+    if p.dim() == 4:
+        v = p.permute(0, 2, 3, 1)
+    elif p.dim() == 5:  # Conv3d (Cout, Cin, KT, 1, 1) -> [Cout, KT, 1, Cin]
+        v = p.permute(0, 2, 3, 4, 1).reshape(p.shape[0], p.shape[2], p.shape[3] * p.shape[4], p.shape[1])
+    elif p.dim() == 2:
+        v = p.unsqueeze(1).unsqueeze(1)  # [out, 1, 1, in]
+    else:
+        raise ValueError(f"unsupported weight rank {p.dim()}")
+    return v
+
+
+def weight_bf16(p):
+    """bf16 compute copy of a weight in kernel layout.  Uses the per-step flat shadow when the model has been
+    prepared by runtime.ParamArena, otherwise casts on the fly (our cast kernel)."""
+    sh = getattr(p, "_t2v_shadow", None)
+    if sh is not None:
+        return sh
+    v = _phys(p.detach())
+    if not v.is_contiguous():
+        v = v.contiguous()
+    if v.dtype == torch.bfloat16:
+        return v
+    return prims.cast_f32_bf16(v.float() if v.dtype != torch.float32 else v)
+
+
+def grad_phys(p):
+    """fp32 accumulation buffer for a weight, in kernel layout (allocates param.grad on first use)."""
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, memory_format=torch.preserve_format)
+    g = _phys(p.grad)
+    if not g.is_contiguous() or g.dtype != torch.float32:
+        raise RuntimeError("parameter gradients must be fp32 with the parameter's own memory format")
+    return g
+
+
+def grad_vec(p):
+    if p.grad is None:
+        p.grad = torch.zeros_like(p)
+    if p.grad.dtype != torch.float32 or not p.grad.is_contiguous():
+        raise RuntimeError("vector parameter gradients must be contiguous fp32")
+    return p.grad
+
+
+def _f32(p):
+    if p is None:
+        return None
+    d = p.detach()
+    return d if d.dtype == torch.float32 else d.float()
+
+
+def _cont(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------- fork / add
+class _Fork(Function):
+    """y_1 = ... = y_n = x.  Backward sums the n incoming gradients with one kernel (instead of autograd's own)."""
+
+    @staticmethod
+    def forward(ctx, x, n):
+        ctx.n = n
+        return tuple(x.view_as(x) for _ in range(n))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        gs = [_cont(g) for g in gs if g is not None]
+        if not gs:
+            return None, None
+        acc = gs[0]
+        i = 1
+        while i < len(gs):
+            if i + 1 < len(gs):
+                acc = prims.add_bf16(acc, gs[i], gs[i + 1])
+                i += 2
+            else:
+                acc = prims.add_bf16(acc, gs[i])
+                i += 1
+        return acc, None
+
+
+def fork(x, n=2):
+    if not x.requires_grad:
+        return (x,) * n
+    return _Fork.apply(x, n)
+
+
+# ---------------------------------------------------------------------------------------------------- conv / linear
+class _Conv(Function):
+    """y = conv(x, W) + bias + rowbias[n // rb_div] + residual on the tcgen05 implicit-GEMM kernel."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, rowbias, residual, stride, pads, rb_div, out_fp32, cin_pad, cout_pad, alpha):
+        w = weight_bf16(weight)
+        if cin_pad or cout_pad:  # 3/4-channel boundary tensors are padded to 8 channels (TMA rows are >= 16 bytes)
+            Co, KH, KW, Ci = w.shape
+            wp = torch.zeros((Co + cout_pad, KH, KW, Ci + cin_pad), device=w.device, dtype=w.dtype)
+            wp[:Co, :, :, :Ci] = w
+            w = wp
+        b = _f32(bias)
+        if b is not None and cout_pad:
+            b = torch.cat([b, b.new_zeros(cout_pad)])
+        y = prims.conv_fwd(x, w, b, rowbias, residual, stride, pads, alpha, out_fp32, rb_div)
+        ctx.save_for_backward(x, w)
+        ctx.weight, ctx.bias = weight, bias
+        ctx.meta = (stride, pads, rb_div, cin_pad, cout_pad, rowbias.shape if rowbias is not None else None,
+                    residual is not None, out_fp32, alpha)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        stride, pads, rb_div, cin_pad, cout_pad, rb_shape, has_res, out_fp32, alpha = ctx.meta
+        weight, bias = ctx.weight, ctx.bias
+        if out_fp32:
+            dy = prims.silu_f32_to_bf16(_cont(dy), apply_silu=False)
+        dy = _cont(dy)
+        N, Ho, Wo, Co = dy.shape
+        d_res = dy if (has_res and ctx.needs_input_grad[4]) else None
+        if alpha != 1.0:
+            assert rb_shape is None and bias is None, "alpha != 1 is only used by bias-free low-rank branches"
+            dy = prims.scale_bf16(dy, alpha)
+        d_rowbias = None
+        if rb_shape is not None and ctx.needs_input_grad[3]:
+            d_rowbias = torch.zeros(rb_shape, device=dy.device, dtype=torch.float32)
+            prims.colsum(dy, d_rowbias, rb_shape[0], (N // rb_shape[0]) * Ho * Wo, Co)
+        if bias is not None and bias.requires_grad:
+            gb = grad_vec(bias)
+            if cout_pad:
+                tmp = torch.zeros(Co, device=dy.device, dtype=torch.float32)
+                prims.colsum(dy, tmp.view(1, Co), 1, N * Ho * Wo, Co)
+                gb += tmp[:Co - cout_pad]
+            elif d_rowbias is not None:
+                prims.colsum_f32(d_rowbias, gb)
+            else:
+                prims.colsum(dy, gb.view(1, Co), 1, N * Ho * Wo, Co)
+        if weight.requires_grad:
+            if cin_pad or cout_pad:
+                tmp = torch.zeros(w.shape, device=dy.device, dtype=torch.float32)
+                prims.conv_wgrad(x, dy, tmp, stride, pads)
+                g = grad_phys(weight)
+                g += tmp[:g.shape[0], :, :, :g.shape[3]]
+            else:
+                prims.conv_wgrad(x, dy, grad_phys(weight), stride, pads)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = prims.conv_dgrad(dy, w, (x.shape[1], x.shape[2]), stride, pads)
+        return dx, None, None, d_rowbias, d_res, None, None, None, None, None, None, None
+
+
+def conv(x, weight, bias=None, rowbias=None, residual=None, stride=1, pads=(1, 1, 1, 1), rb_div=1, out_fp32=False,
+         cin_pad=0, cout_pad=0, alpha=1.0):
+    return _Conv.apply(x, weight, bias, rowbias, residual, stride, tuple(pads), rb_div, out_fp32, cin_pad, cout_pad, float(alpha))
+
+
+def linear(x, weight, bias=None, residual=None, out_fp32=False, alpha=1.0):
+    """x [rows, in] -> [rows, out] through the same kernel (a 1x1 convolution over a rows x 1 image)."""
+    rows, cin = x.shape
+    res4 = residual.view(1, 1, rows, -1) if residual is not None else None
+    y = _Conv.apply(x.view(1, 1, rows, cin), weight, bias, None, res4, 1, (0, 0, 0, 0), 1, out_fp32, 0, 0, float(alpha))
+    return y.view(rows, -1)
+
+
+# ---------------------------------------------------------------------------------------------------- norms
+class _GroupNorm(Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, eps, silu, samples):
+        shape = x.shape
+        C = shape[-1]
+        x3 = x.view(samples, -1, C)
+        g32, b32 = _f32(gamma), _f32(beta)
+        y, stat, ab = prims.groupnorm_fwd(x3, g32, b32, groups, eps, silu)
+        ctx.save_for_backward(x3, g32, stat, ab)
+        ctx.gamma, ctx.beta = gamma, beta
+        ctx.meta = (groups, silu, shape)
+        return y.view(shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x3, g32, stat, ab = ctx.saved_tensors
+        groups, silu, shape = ctx.meta
+        dgamma = grad_vec(ctx.gamma) if ctx.gamma.requires_grad else None
+        dbeta = grad_vec(ctx.beta) if ctx.beta.requires_grad else None
+        dx = prims.groupnorm_bwd(_cont(dy).view(x3.shape), x3, g32, stat, ab, groups, silu, None, dgamma, dbeta)
+        return dx.view(shape), None, None, None, None, None, None
+
+
+def group_norm(x, gamma, beta, groups, eps, silu, samples):
+    """x [..., C] with `samples` independent normalisation samples (frames or clips) along the leading dims."""
+    return _GroupNorm.apply(x, gamma, beta, groups, eps, silu, samples)
+
+
+class _LayerNorm(Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        g32, b32 = _f32(gamma), _f32(beta)
+        y, stat = prims.layernorm_fwd(x, g32, b32, eps)
+        ctx.save_for_backward(x, g32, stat)
+        ctx.gamma, ctx.beta = gamma, beta
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g32, stat = ctx.saved_tensors
+        dgamma = grad_vec(ctx.gamma) if ctx.gamma.requires_grad else None
+        dbeta = grad_vec(ctx.beta) if ctx.beta.requires_grad else None
+        return prims.layernorm_bwd(_cont(dy), x, g32, stat, None, dgamma, dbeta), None, None, None
+
+
+def layer_norm(x, gamma, beta, eps=1e-5):
+    return _LayerNorm.apply(x, gamma, beta, eps)
+
+
+# ---------------------------------------------------------------------------------------------------- activations
+class _Geglu(Function):
+    @staticmethod
+    def forward(ctx, proj):
+        ctx.save_for_backward(proj)
+        return prims.geglu_fwd(proj)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (proj,) = ctx.saved_tensors
+        return prims.geglu_bwd(proj, _cont(dout))
+
+
+def geglu(proj):
+    return _Geglu.apply(proj)
+
+
+class _Silu(Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return prims.silu_bf16(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return prims.silu_bf16_bwd(x, _cont(dy))
+
+
+def silu(x):
+    return _Silu.apply(x)
+
+
+# ---------------------------------------------------------------------------------------------------- resampling / concat
+class _Upsample(Function):
+    @staticmethod
+    def forward(ctx, x, out_hw):
+        ctx.in_hw = (x.shape[1], x.shape[2])
+        return prims.upsample_nearest_fwd(x, out_hw)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return prims.upsample_nearest_bwd(_cont(dy), ctx.in_hw), None
+
+
+def upsample_nearest(x, out_hw):
+    return _Upsample.apply(x, tuple(out_hw))
+
+
+class _Concat(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.ca = a.shape[-1]
+        return prims.concat_channels(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        return prims.split_channels(_cont(g), ctx.ca)
+
+
+def concat_channels(a, b):
+    return _Concat.apply(a, b)
+
+
+# ---------------------------------------------------------------------------------------------------- attention
+def _rup8(n):
+    return (n + 7) // 8 * 8
+
+
+class _Attention(Function):
+    """softmax(q k^T / sqrt(d)) v for token matrices q [Nb, Lq, H*D], k/v [Nb, Lk, H*D]; the four contractions run
+    as batched GEMMs on the tcgen05 kernel, the row softmax in between as one HBM-bound pass."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, heads):
+        Nb, Lq, C = q.shape
+        Lk = k.shape[1]
+        D = C // heads
+        ld = _rup8(Lk)
+        scale = D ** -0.5
+        s = torch.empty((Nb, heads, Lq, ld), device=q.device, dtype=torch.float32)
+        prims.bgemm(q, (1, C, Lq * C, D), k, (1, C, Lk * C, D), s, (ld, heads * Lq * ld, Lq * ld), Lq, Lk, D, Nb, heads, scale, 1)
+        p = prims.softmax_fwd(s, Lk, ld)
+        del s
+        o = torch.empty_like(q)
+        prims.bgemm(p, (1, ld, heads * Lq * ld, Lq * ld), v, (0, C, Lk * C, D), o, (C, Lq * C, D), Lq, D, Lk, Nb, heads, 1.0, 0)
+        ctx.save_for_backward(q, k, v, p)
+        ctx.heads = heads
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, p = ctx.saved_tensors
+        heads = ctx.heads
+        do = _cont(do)
+        Nb, Lq, C = q.shape
+        Lk = k.shape[1]
+        D = C // heads
+        ld = p.shape[-1]
+        scale = D ** -0.5
+        pd = (ld, heads * Lq * ld, Lq * ld)
+        dv = torch.empty_like(v)  # dV = P^T dO
+        prims.bgemm(p, (0,) + pd, do, (0, C, Lq * C, D), dv, (C, Lk * C, D), Lk, D, Lq, Nb, heads, 1.0, 0)
+        dp = torch.empty((Nb, heads, Lq, ld), device=q.device, dtype=torch.float32)  # dP = dO V^T
+        prims.bgemm(do, (1, C, Lq * C, D), v, (1, C, Lk * C, D), dp, pd, Lq, Lk, D, Nb, heads, 1.0, 1)
+        ds = prims.softmax_bwd(p, dp, Lk, scale)
+        del dp
+        dq = torch.empty_like(q)  # dQ = dS K
+        prims.bgemm(ds, (1,) + pd, k, (0, C, Lk * C, D), dq, (C, Lq * C, D), Lq, D, Lk, Nb, heads, 1.0, 0)
+        dk = torch.empty_like(k)  # dK = dS^T Q
+        prims.bgemm(ds, (0,) + pd, q, (0, C, Lq * C, D), dk, (C, Lk * C, D), Lk, D, Lq, Nb, heads, 1.0, 0)
+        return dq, dk, dv, None
+
+
+def attention(q, k, v, heads):
+    return _Attention.apply(q, k, v, heads)
+
+
+class _TemporalAttention(Function):
+    """Self-attention along the frame axis on frames-major tokens [B*F*HW, H*D] (no permute; see attn_small.cu)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, heads, B, F, HW):
+        C = q.shape[-1]
+        D = C // heads
+        addr = (B * HW, HW, F * HW * C, C, HW * C, heads, F, D)
+        ctx.addr = addr
+        ctx.save_for_backward(q, k, v)
+        return prims.attn_small_fwd(q, k, v, *addr)
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v = ctx.saved_tensors
+        dq, dk, dv = prims.attn_small_bwd(q, k, v, _cont(do), *ctx.addr)
+        return dq, dk, dv, None, None, None, None
+
+
+def temporal_attention(q, k, v, heads, B, F, HW):
+    return _TemporalAttention.apply(q, k, v, heads, B, F, HW)
+
+
+# ---------------------------------------------------------------------------------------------------- latent boundary
+class _FromNhwc8(Function):
+    """[B*F, H, W, 8] bf16 -> (B, C, F, H, W) fp32 (the `.sample` layout of UNet3DConditionModel.forward)."""
+
+    @staticmethod
+    def forward(ctx, x, B, C, F):
+        ctx.meta = (B, C, F)
+        return prims.nhwc8_to_latents(x, B, C, F)
+
+    @staticmethod
+    def backward(ctx, g):
+        return prims.latents_to_nhwc8(_cont(g.float())), None, None, None
+
+
+def from_nhwc8(x, B, C, F):
+    return _FromNhwc8.apply(x, B, C, F)
+
+
+class _MseLoss(Function):
+    """mean((pred - target)^2) in fp32 straight from the channels-last prediction (train.py:827)."""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        ctx.save_for_backward(pred, target)
+        return prims.mse_loss_fwd(pred, target)
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, target = ctx.saved_tensors
+        return prims.mse_loss_bwd(pred, target, _cont(g.float())), None
+
+
+def mse_loss_nhwc8(pred, target):
+    return _MseLoss.apply(pred, target)

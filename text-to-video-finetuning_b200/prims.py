@@ -1,0 +1,339 @@
+"""Tensor-level wrappers over the C ABI (include/t2v_b200.h): each function takes/returns torch CUDA tensors, allocates
+outputs with PyTorch's caching allocator and launches on torch's current stream.  No autograd here (see ops.py) and
+no fallback: every function ends in a native call.
+
+Layout contract: activations are bf16 channels-last `[N, H, W, C]` (or `[rows, C]` token matrices), convolution
+weights are bf16 `[Cout, KH, KW, Cin]`, statistics / biases / parameter gradients are fp32.
+"""
+import ctypes
+
+import torch
+
+from . import native
+
+_VP = ctypes.c_void_p
+
+
+def _p(t):
+    return _VP(0) if t is None else _VP(t.data_ptr())
+
+
+def _stream():
+    return _VP(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk_bf16(*ts):
+    for t in ts:
+        if t is not None:
+            assert t.dtype == torch.bfloat16 and t.is_contiguous() and t.is_cuda, (t.dtype, t.shape, t.stride(), t.device)
+
+
+def _chk_f32(*ts):
+    for t in ts:
+        if t is not None:
+            assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda, (t.dtype, t.shape, t.stride())
+
+
+def out_hw(H, W, KH, KW, stride, pads):
+    return (H + pads[0] + pads[1] - KH) // stride + 1, (W + pads[2] + pads[3] - KW) // stride + 1
+
+
+# ---------------------------------------------------------------------------------------------- tensor-core family
+def conv_fwd(x, w, bias=None, rowbias=None, residual=None, stride=1, pads=(0, 0, 0, 0), alpha=1.0, out_fp32=False, rowbias_div=1):
+    """x [N,H,W,Ci] bf16, w [Co,KH,KW,Ci] bf16 -> y [N,Ho,Wo,Co]; y = alpha*conv + bias[c] + rowbias[n,c] + residual."""
+    _chk_bf16(x, w, residual)
+    _chk_f32(bias, rowbias)
+    N, H, W, Ci = x.shape
+    Co, KH, KW, Ci2 = w.shape
+    assert Ci == Ci2, (x.shape, w.shape)
+    Ho, Wo = out_hw(H, W, KH, KW, stride, pads)
+    y = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    epi = native.Epilogue(bias.data_ptr() if bias is not None else None, rowbias.data_ptr() if rowbias is not None else None,
+                          residual.data_ptr() if residual is not None else None, float(alpha), int(out_fp32), int(rowbias_div))
+    native.check(native.lib().t2v_conv_fwd(_p(x), _p(w), _p(y), N, H, W, Ci, Co, KH, KW, stride, *pads, ctypes.byref(epi), _stream()))
+    return y
+
+
+def conv_dgrad(dy, w, in_hw, stride=1, pads=(0, 0, 0, 0), residual=None):
+    """dy [N,Ho,Wo,Co] -> dx [N,H,W,Ci] (+ residual, which may alias nothing)."""
+    _chk_bf16(dy, w, residual)
+    N = dy.shape[0]
+    H, W = in_hw
+    Co, KH, KW, Ci = w.shape
+    dx = torch.empty((N, H, W, Ci), device=dy.device, dtype=torch.bfloat16)
+    epi = native.Epilogue(None, None, residual.data_ptr() if residual is not None else None, 1.0, 0, 1)
+    native.check(native.lib().t2v_conv_dgrad(_p(dy), _p(w), _p(dx), N, H, W, Ci, Co, KH, KW, stride, *pads, ctypes.byref(epi), _stream()))
+    return dx
+
+
+def conv_wgrad(x, dy, dw, stride=1, pads=(0, 0, 0, 0)):
+    """dw [Co,KH,KW,Ci] fp32 += dy^T * shifted(x)."""
+    _chk_bf16(x, dy)
+    _chk_f32(dw)
+    N, H, W, Ci = x.shape
+    Co, KH, KW, Ci2 = dw.shape
+    assert Ci2 == Ci and dy.shape[-1] == Co
+    native.check(native.lib().t2v_conv_wgrad(_p(x), _p(dy), _p(dw), N, H, W, Ci, Co, KH, KW, stride, *pads, _stream()))
+
+
+def _mat(t, kmajor, ld, s1, s2):
+    return native.Mat(t.data_ptr(), ld, s1, s2, int(kmajor))
+
+
+def bgemm(a, a_desc, b, b_desc, c, c_desc, M, N, K, Z1, Z2, alpha=1.0, out_mode=0):
+    """Raw strided-batched GEMM; *_desc = (kmajor, ld, stride_z1, stride_z2) / c_desc = (ld, stride_z1, stride_z2)."""
+    mA, mB = _mat(a, *a_desc), _mat(b, *b_desc)
+    native.check(native.lib().t2v_bgemm(ctypes.byref(mA), ctypes.byref(mB), _p(c), c_desc[0], c_desc[1], c_desc[2],
+                                        M, N, K, Z1, Z2, float(alpha), out_mode, _stream()))
+
+
+# ---------------------------------------------------------------------------------------------- norms
+def groupnorm_ws(S, P, C, device):
+    n = native.lib().t2v_groupnorm_workspace_bytes(S, P, C)
+    return torch.empty((n + 3) // 4, device=device, dtype=torch.float32)
+
+
+def groupnorm_fwd(x, gamma, beta, G, eps, silu):
+    """x [S,P,C] bf16 -> y, stat [S,G,2], ab [S,C,2]."""
+    _chk_bf16(x)
+    _chk_f32(gamma, beta)
+    S, P, C = x.shape
+    y = torch.empty_like(x)
+    stat = torch.empty((S, G, 2), device=x.device, dtype=torch.float32)
+    ab = torch.empty((S, C, 2), device=x.device, dtype=torch.float32)
+    ws = groupnorm_ws(S, P, C, x.device)
+    native.check(native.lib().t2v_groupnorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(stat), _p(ab), _p(ws), S, P, C, G, float(eps),
+                                                int(silu), _stream()))
+    return y, stat, ab
+
+
+def groupnorm_bwd(dy, x, gamma, stat, ab, G, silu, add=None, dgamma=None, dbeta=None):
+    _chk_bf16(dy, x, add)
+    S, P, C = x.shape
+    dx = torch.empty_like(x)
+    ws = groupnorm_ws(S, P, C, x.device)
+    native.check(native.lib().t2v_groupnorm_bwd(_p(dy), _p(x), _p(gamma), _p(stat), _p(ab), _p(add), _p(dx), _p(dgamma), _p(dbeta),
+                                                _p(ws), S, P, C, G, int(silu), _stream()))
+    return dx
+
+
+def layernorm_fwd(x, gamma, beta, eps):
+    _chk_bf16(x)
+    rows, C = x.shape
+    y = torch.empty_like(x)
+    stat = torch.empty((rows, 2), device=x.device, dtype=torch.float32)
+    native.check(native.lib().t2v_layernorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(stat), rows, C, float(eps), _stream()))
+    return y, stat
+
+
+def layernorm_bwd(dy, x, gamma, stat, add=None, dgamma=None, dbeta=None):
+    _chk_bf16(dy, x, add)
+    rows, C = x.shape
+    dx = torch.empty_like(x)
+    native.check(native.lib().t2v_layernorm_bwd(_p(dy), _p(x), _p(gamma), _p(stat), _p(add), _p(dx), _p(dgamma), _p(dbeta), rows, C, _stream()))
+    return dx
+
+
+# ---------------------------------------------------------------------------------------------- elementwise / glue
+def geglu_fwd(proj):
+    _chk_bf16(proj)
+    M, I2 = proj.shape
+    out = torch.empty((M, I2 // 2), device=proj.device, dtype=torch.bfloat16)
+    native.check(native.lib().t2v_geglu_fwd(_p(proj), _p(out), M, I2 // 2, _stream()))
+    return out
+
+
+def geglu_bwd(proj, dout):
+    _chk_bf16(proj, dout)
+    M, I2 = proj.shape
+    dproj = torch.empty_like(proj)
+    native.check(native.lib().t2v_geglu_bwd(_p(proj), _p(dout), _p(dproj), M, I2 // 2, _stream()))
+    return dproj
+
+
+def silu_f32_to_bf16(x, apply_silu=True):
+    _chk_f32(x)
+    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    native.check(native.lib().t2v_silu_f32_to_bf16(_p(x), _p(y), x.numel(), int(apply_silu), _stream()))
+    return y
+
+
+def silu_bwd_f32(x, dy):
+    _chk_f32(x, dy)
+    dx = torch.empty_like(x)
+    native.check(native.lib().t2v_silu_bwd_f32(_p(x), _p(dy), _p(dx), x.numel(), 0, _stream()))
+    return dx
+
+
+def silu_bf16(x):
+    _chk_bf16(x)
+    y = torch.empty_like(x)
+    native.check(native.lib().t2v_silu_bf16(_p(x), _p(y), x.numel(), _stream()))
+    return y
+
+
+def silu_bf16_bwd(x, dy):
+    _chk_bf16(x, dy)
+    dx = torch.empty_like(x)
+    native.check(native.lib().t2v_silu_bf16_bwd(_p(x), _p(dy), _p(dx), x.numel(), _stream()))
+    return dx
+
+
+def add_bf16(a, b, c=None):
+    _chk_bf16(a, b, c)
+    out = torch.empty_like(a)
+    native.check(native.lib().t2v_add_bf16(_p(a), _p(b), _p(c), _p(out), a.numel(), _stream()))
+    return out
+
+
+def scale_bf16(a, alpha):
+    """alpha * a (bf16) - expressed as the add kernel's sibling via a 1x1 identity would be wasteful; uses add with itself
+    is wrong for general alpha, so this has its own tiny kernel."""
+    _chk_bf16(a)
+    out = torch.empty_like(a)
+    native.check(native.lib().t2v_scale_bf16(_p(a), _p(out), a.numel(), float(alpha), _stream()))
+    return out
+
+
+def add_f32(a, b):
+    _chk_f32(a, b)
+    out = torch.empty_like(a)
+    native.check(native.lib().t2v_add_f32(_p(a), _p(b), _p(out), a.numel(), _stream()))
+    return out
+
+
+def cast_f32_bf16(src, dst=None):
+    assert src.dtype == torch.float32 and src.is_cuda
+    if dst is None:
+        dst = torch.empty(src.shape, device=src.device, dtype=torch.bfloat16)
+    native.check(native.lib().t2v_cast_f32_bf16(_p(src), _p(dst), src.numel(), _stream()))
+    return dst
+
+
+def upsample_nearest_fwd(x, out_hw_):
+    _chk_bf16(x)
+    N, H, W, C = x.shape
+    Ho, Wo = out_hw_
+    y = torch.empty((N, Ho, Wo, C), device=x.device, dtype=torch.bfloat16)
+    native.check(native.lib().t2v_upsample_nearest_fwd(_p(x), _p(y), N, H, W, Ho, Wo, C, _stream()))
+    return y
+
+
+def upsample_nearest_bwd(dy, in_hw):
+    _chk_bf16(dy)
+    N, Ho, Wo, C = dy.shape
+    H, W = in_hw
+    dx = torch.empty((N, H, W, C), device=dy.device, dtype=torch.bfloat16)
+    native.check(native.lib().t2v_upsample_nearest_bwd(_p(dy), _p(dx), N, H, W, Ho, Wo, C, _stream()))
+    return dx
+
+
+def copy_cols(src, dst, M, C, src_ld, src_off, dst_ld, dst_off):
+    native.check(native.lib().t2v_copy_cols(_p(src), _p(dst), M, C, src_ld, src_off, dst_ld, dst_off, _stream()))
+
+
+def concat_channels(a, b):
+    """[..., Ca] ++ [..., Cb] along the (contiguous) channel axis."""
+    _chk_bf16(a, b)
+    Ca, Cb = a.shape[-1], b.shape[-1]
+    M = a.numel() // Ca
+    out = torch.empty(a.shape[:-1] + (Ca + Cb,), device=a.device, dtype=torch.bfloat16)
+    copy_cols(a, out, M, Ca, Ca, 0, Ca + Cb, 0)
+    copy_cols(b, out, M, Cb, Cb, 0, Ca + Cb, Ca)
+    return out
+
+
+def split_channels(g, Ca):
+    _chk_bf16(g)
+    Ct = g.shape[-1]
+    M = g.numel() // Ct
+    a = torch.empty(g.shape[:-1] + (Ca,), device=g.device, dtype=torch.bfloat16)
+    b = torch.empty(g.shape[:-1] + (Ct - Ca,), device=g.device, dtype=torch.bfloat16)
+    copy_cols(g, a, M, Ca, Ct, 0, Ca, 0)
+    copy_cols(g, b, M, Ct - Ca, Ct, Ca, Ct - Ca, 0)
+    return a, b
+
+
+def colsum(x, out, S, P, C):
+    """out [S,C] fp32 += sum over P of x [S,P,C] bf16."""
+    _chk_bf16(x)
+    _chk_f32(out)
+    native.check(native.lib().t2v_colsum(_p(x), _p(out), S, P, C, _stream()))
+
+
+def colsum_f32(x, out):
+    _chk_f32(x, out)
+    native.check(native.lib().t2v_colsum_f32(_p(x), _p(out), x.shape[0], x.shape[1], _stream()))
+
+
+def softmax_fwd(s, n_valid, ld_out):
+    _chk_f32(s)
+    rows = s.numel() // s.shape[-1]
+    p = torch.empty(s.shape[:-1] + (ld_out,), device=s.device, dtype=torch.bfloat16)
+    native.check(native.lib().t2v_softmax_fwd(_p(s), _p(p), rows, n_valid, s.shape[-1], ld_out, _stream()))
+    return p
+
+
+def softmax_bwd(p, dp, n_valid, scale):
+    _chk_bf16(p)
+    _chk_f32(dp)
+    rows = p.numel() // p.shape[-1]
+    ds = torch.empty_like(p)
+    native.check(native.lib().t2v_softmax_bwd(_p(p), _p(dp), _p(ds), rows, n_valid, p.shape[-1], dp.shape[-1], float(scale), _stream()))
+    return ds
+
+
+def attn_small_fwd(q, k, v, nseq, inner, outer_stride, inner_stride, seq_stride, heads, L, D):
+    _chk_bf16(q, k, v)
+    o = torch.empty_like(q)
+    native.check(native.lib().t2v_attn_small_fwd(_p(q), _p(k), _p(v), _p(o), nseq, inner, outer_stride, inner_stride, seq_stride,
+                                                 heads, L, D, _stream()))
+    return o
+
+
+def attn_small_bwd(q, k, v, do, nseq, inner, outer_stride, inner_stride, seq_stride, heads, L, D):
+    _chk_bf16(q, k, v, do)
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    native.check(native.lib().t2v_attn_small_bwd(_p(q), _p(k), _p(v), _p(do), _p(dq), _p(dk), _p(dv), nseq, inner, outer_stride,
+                                                 inner_stride, seq_stride, heads, L, D, _stream()))
+    return dq, dk, dv
+
+
+def timestep_embedding(t, dim):
+    assert t.dtype == torch.int64 and t.is_cuda
+    out = torch.empty((t.shape[0], dim), device=t.device, dtype=torch.bfloat16)
+    native.check(native.lib().t2v_timestep_embedding(_p(t), _p(out), t.shape[0], dim, _stream()))
+    return out
+
+
+def latents_to_nhwc8(x0, noise=None, alphas_cumprod=None, timesteps=None):
+    """(B,C,F,H,W) fp32 [-> add_noise] -> [B*F,H,W,8] bf16."""
+    _chk_f32(x0, noise, alphas_cumprod)
+    B, C, F, H, W = x0.shape
+    out = torch.empty((B * F, H, W, 8), device=x0.device, dtype=torch.bfloat16)
+    native.check(native.lib().t2v_latents_to_nhwc8(_p(x0), _p(noise), _p(alphas_cumprod), _p(timesteps), _p(out), B, C, F, H * W, _stream()))
+    return out
+
+
+def nhwc8_to_latents(x, B, C, F):
+    _chk_bf16(x)
+    _, H, W, _ = x.shape
+    out = torch.empty((B, C, F, H, W), device=x.device, dtype=torch.float32)
+    native.check(native.lib().t2v_nhwc8_to_latents(_p(x), _p(out), B, C, F, H * W, _stream()))
+    return out
+
+
+def mse_loss_fwd(pred, target):
+    _chk_bf16(pred)
+    _chk_f32(target)
+    B, C, F, H, W = target.shape
+    loss = torch.empty((), device=pred.device, dtype=torch.float32)
+    native.check(native.lib().t2v_mse_loss(_p(pred), _p(target), _p(loss), _p(None), _p(None), B, C, F, H * W, _stream()))
+    return loss
+
+
+def mse_loss_bwd(pred, target, gout):
+    B, C, F, H, W = target.shape
+    dpred = torch.empty_like(pred)
+    native.check(native.lib().t2v_mse_loss(_p(pred), _p(target), _p(None), _p(gout), _p(dpred), B, C, F, H * W, _stream()))
+    return dpred
