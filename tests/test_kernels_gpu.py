@@ -1,0 +1,195 @@
+"""Per-kernel GPU parity: every HBM-bound sm_100a kernel vs its plain-PyTorch fp32 restatement (oracle/ops_ref.py)
+on the same seeded inputs, through the C ABI.  Floating point: tolerances are bf16 output rounding (2^-8) or tighter."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _mods():
+    from oracle import ops_ref
+    from t2v_b200 import prims
+    return prims, ops_ref
+
+
+def _gen(seed=0):
+    return torch.Generator(device=DEV).manual_seed(seed)
+
+
+def rnd(g, *shape, scale=1.0, dtype=torch.bfloat16):
+    return (torch.randn(*shape, device=DEV, generator=g) * scale).to(dtype)
+
+
+def close(a, b, tol, what=""):
+    a, b = a.float(), b.float()
+    err = (a - b).abs().max().item() / max(b.abs().max().item(), 1e-6)
+    assert err < tol, f"{what}: rel-to-max error {err:.3e} >= {tol}"
+
+
+@pytest.mark.parametrize("S,P,C,G,silu", [(16, 1024, 320, 32, 1), (1, 4096, 640, 32, 1), (2, 64, 2560, 32, 1), (4, 100, 64, 32, 0),
+                                          (3, 17, 1280, 32, 0), (1, 16384, 128, 32, 1)])
+def test_groupnorm(S, P, C, G, silu):
+    prims, ref = _mods()
+    g = _gen(1)
+    x = rnd(g, S, P, C) * 2 + 0.5
+    gamma = 1 + 0.2 * torch.randn(C, device=DEV, generator=g)
+    beta = 0.1 * torch.randn(C, device=DEV, generator=g)
+    eps = 1e-5
+    y, stat, ab = prims.groupnorm_fwd(x, gamma, beta, G, eps, silu)
+    y_r, stat_r, ab_r = ref.groupnorm_fwd(x, gamma, beta, G, eps, silu)
+    close(y, y_r, 1e-2, "gn y")
+    close(stat, stat_r, 1e-3, "gn stat")
+    close(ab, ab_r, 1e-3, "gn ab")
+    dy = rnd(g, S, P, C)
+    add = rnd(g, S, P, C)
+    dg, db = torch.ones(C, device=DEV), torch.ones(C, device=DEV)
+    dg_r, db_r = dg.clone(), db.clone()
+    dx = prims.groupnorm_bwd(dy, x, gamma, stat, ab, G, silu, add, dg, db)
+    dx_r = ref.groupnorm_bwd(dy, x, gamma, stat_r, ab_r, G, silu, add, dg_r, db_r)
+    close(dx, dx_r, 1.5e-2, "gn dx")
+    close(dg, dg_r, 3e-3, "gn dgamma")
+    close(db, db_r, 3e-3, "gn dbeta")
+
+
+@pytest.mark.parametrize("rows,C", [(16384, 320), (4096, 640), (1000, 1280), (77, 512), (5, 64), (300, 2048)])
+def test_layernorm(rows, C):
+    prims, ref = _mods()
+    g = _gen(2)
+    x = rnd(g, rows, C) * 1.5 + 0.3
+    gamma = 1 + 0.2 * torch.randn(C, device=DEV, generator=g)
+    beta = 0.1 * torch.randn(C, device=DEV, generator=g)
+    y, stat = prims.layernorm_fwd(x, gamma, beta, 1e-5)
+    y_r, stat_r = ref.layernorm_fwd(x, gamma, beta, 1e-5)
+    close(y, y_r, 1e-2, "ln y")
+    close(stat, stat_r, 1e-4, "ln stat")
+    dy, add = rnd(g, rows, C), rnd(g, rows, C)
+    dg, db = torch.ones(C, device=DEV), torch.ones(C, device=DEV)
+    dg_r, db_r = dg.clone(), db.clone()
+    dx = prims.layernorm_bwd(dy, x, gamma, stat, add, dg, db)
+    dx_r = ref.layernorm_bwd(dy, x, gamma, stat_r, add, dg_r, db_r)
+    close(dx, dx_r, 1.5e-2, "ln dx")
+    close(dg, dg_r, 3e-3, "ln dgamma")
+    close(db, db_r, 3e-3, "ln dbeta")
+
+
+def test_geglu_silu_add_scale_cast():
+    prims, ref = _mods()
+    g = _gen(3)
+    proj = rnd(g, 1000, 2560, scale=2.0)
+    close(prims.geglu_fwd(proj), ref.geglu_fwd(proj), 1e-2, "geglu")
+    dout = rnd(g, 1000, 1280)
+    close(prims.geglu_bwd(proj, dout), ref.geglu_bwd(proj, dout), 1e-2, "geglu bwd")
+    x = rnd(g, 3, 1280, scale=3.0)
+    close(prims.silu_bf16(x), ref.silu_bf16(x), 1e-2, "silu")
+    close(prims.silu_bf16_bwd(x, x), ref.silu_bf16_bwd(x, x), 1e-2, "silu bwd")
+    xf = torch.randn(3, 1280, device=DEV, generator=g)
+    close(prims.silu_f32_to_bf16(xf), ref.silu_f32_to_bf16(xf), 1e-2, "silu f32")
+    close(prims.silu_bwd_f32(xf, xf), ref.silu_bwd_f32(xf, xf), 1e-4, "silu bwd f32")
+    a, b, c = rnd(g, 40, 64), rnd(g, 40, 64), rnd(g, 40, 64)
+    close(prims.add_bf16(a, b, c), ref.add_bf16(a, b, c), 1e-2, "add3")
+    close(prims.add_bf16(a, b), ref.add_bf16(a, b), 1e-2, "add2")
+    close(prims.scale_bf16(a, 0.37), ref.scale_bf16(a, 0.37), 1e-2, "scale")
+    src = torch.randn(1003, device=DEV, generator=g)
+    assert torch.equal(prims.cast_f32_bf16(src), src.bfloat16())
+
+
+@pytest.mark.parametrize("N,H,W,Ho,Wo,C", [(4, 8, 8, 16, 16, 64), (2, 2, 2, 3, 3, 128), (1, 5, 9, 10, 18, 8)])
+def test_upsample(N, H, W, Ho, Wo, C):
+    prims, ref = _mods()
+    g = _gen(4)
+    x = rnd(g, N, H, W, C)
+    assert torch.equal(prims.upsample_nearest_fwd(x, (Ho, Wo)), ref.upsample_nearest_fwd(x, (Ho, Wo)))
+    dy = rnd(g, N, Ho, Wo, C)
+    close(prims.upsample_nearest_bwd(dy, (H, W)), ref.upsample_nearest_bwd(dy, (H, W)), 1e-2, "upsample bwd")
+
+
+def test_concat_split_colsum():
+    prims, ref = _mods()
+    g = _gen(5)
+    a, b = rnd(g, 6, 5, 7, 320), rnd(g, 6, 5, 7, 640)
+    cat = prims.concat_channels(a, b)
+    assert torch.equal(cat, torch.cat([a, b], -1))
+    a2, b2 = prims.split_channels(cat, 320)
+    assert torch.equal(a2, a) and torch.equal(b2, b)
+    x = rnd(g, 4, 300, 320)
+    out, out_r = torch.ones(4, 320, device=DEV), torch.ones(4, 320, device=DEV)
+    prims.colsum(x, out, 4, 300, 320)
+    ref.colsum(x, out_r, 4, 300, 320)
+    close(out, out_r, 1e-3, "colsum")
+    acc, acc_r = torch.ones(320, device=DEV), torch.ones(320, device=DEV)
+    prims.colsum_f32(out, acc)
+    ref.colsum_f32(out_r, acc_r)
+    close(acc, acc_r, 1e-3, "colsum_f32")
+
+
+@pytest.mark.parametrize("rows,n,ld", [(5000, 77, 80), (2048, 1024, 1024), (33, 16, 16)])
+def test_softmax(rows, n, ld):
+    prims, ref = _mods()
+    g = _gen(6)
+    s = torch.randn(rows, ld, device=DEV, generator=g) * 4
+    p = prims.softmax_fwd(s, n, ld)
+    p_r = ref.softmax_fwd(s, n, ld)
+    close(p, p_r, 1e-2, "softmax")
+    assert (p[:, n:] == 0).all()
+    dp = torch.randn(rows, ld, device=DEV, generator=g)
+    close(prims.softmax_bwd(p_r, dp, n, 0.125), ref.softmax_bwd(p_r, dp, n, 0.125), 1e-2, "softmax bwd")
+
+
+@pytest.mark.parametrize("B,F,HW,heads,D", [(1, 16, 64, 5, 64), (2, 8, 16, 2, 64), (1, 24, 9, 1, 32), (1, 32, 4, 8, 64), (1, 1, 16, 2, 64)])
+def test_temporal_attention(B, F, HW, heads, D):
+    prims, ref = _mods()
+    g = _gen(7)
+    C = heads * D
+    q, k, v, do = (rnd(g, B * F * HW, C) for _ in range(4))
+    addr = (B * HW, HW, F * HW * C, C, HW * C, heads, F, D)
+    close(prims.attn_small_fwd(q, k, v, *addr), ref.attn_small_fwd(q, k, v, *addr), 1e-2, "attn_small fwd")
+    got = prims.attn_small_bwd(q, k, v, do, *addr)
+    exp = ref.attn_small_bwd(q, k, v, do, *addr)
+    for name, a, b in zip("qkv", got, exp):
+        close(a, b, 1.5e-2, f"attn_small d{name}")
+
+
+def test_latent_boundary_and_loss():
+    prims, ref = _mods()
+    g = _gen(8)
+    B, C, F, H, W = 2, 4, 3, 8, 12
+    x0 = torch.randn(B, C, F, H, W, device=DEV, generator=g)
+    noise = torch.randn(B, C, F, H, W, device=DEV, generator=g)
+    abar = torch.linspace(0.999, 0.01, 1000, device=DEV)
+    t = torch.tensor([7, 912], device=DEV)
+    close(prims.latents_to_nhwc8(x0), ref.latents_to_nhwc8(x0), 1e-2, "to_nhwc8")
+    xn = prims.latents_to_nhwc8(x0, noise, abar, t)
+    close(xn, ref.latents_to_nhwc8(x0, noise, abar, t), 1e-2, "add_noise")
+    assert (xn[..., C:] == 0).all()
+    assert torch.equal(prims.nhwc8_to_latents(xn, B, C, F), ref.nhwc8_to_latents(xn, B, C, F))
+    loss, loss_r = prims.mse_loss_fwd(xn, noise), ref.mse_loss_fwd(xn, noise)
+    assert abs(loss.item() - loss_r.item()) < 1e-5 * abs(loss_r.item()) + 1e-7
+    gout = torch.tensor(1.7, device=DEV)
+    close(prims.mse_loss_bwd(xn, noise, gout), ref.mse_loss_bwd(xn, noise, gout), 1e-2, "mse bwd")
+    tt = torch.tensor([0, 1, 500, 999], device=DEV)
+    close(prims.timestep_embedding(tt, 320), ref.timestep_embedding(tt, 320), 1e-2, "timestep emb")
+
+
+@pytest.mark.parametrize("Nb,Lq,Lk,heads,D", [(4, 256, 256, 2, 64), (2, 1024, 77, 5, 64), (3, 64, 64, 1, 512), (2, 100, 36, 3, 64)])
+def test_attention_composite(Nb, Lq, Lk, heads, D):
+    """ops.attention (4 tcgen05 batched GEMMs + softmax) vs torch reference, forward and backward."""
+    from t2v_b200 import ops
+    g = _gen(9)
+    C = heads * D
+    q = rnd(g, Nb, Lq, C).requires_grad_(True)
+    k = rnd(g, Nb, Lk, C).requires_grad_(True)
+    v = rnd(g, Nb, Lk, C).requires_grad_(True)
+    do = rnd(g, Nb, Lq, C)
+    o = ops.attention(q, k, v, heads)
+    o.backward(do)
+    qf, kf, vf = (t.detach().float().requires_grad_(True) for t in (q, k, v))
+    Q = qf.view(Nb, Lq, heads, D).transpose(1, 2)
+    K = kf.view(Nb, Lk, heads, D).transpose(1, 2)
+    V = vf.view(Nb, Lk, heads, D).transpose(1, 2)
+    O = (torch.softmax(Q @ K.transpose(-1, -2) * D ** -0.5, -1) @ V).transpose(1, 2).reshape(Nb, Lq, C)
+    O.backward(do.float())
+    close(o, O, 1.5e-2, "attention o")
+    close(q.grad, qf.grad, 2e-2, "attention dq")
+    close(k.grad, kf.grad, 2e-2, "attention dk")
+    close(v.grad, vf.grad, 2e-2, "attention dv")

@@ -194,8 +194,13 @@ int t2v_attn_small_fwd(const void* q, const void* k, const void* v, void* o, int
     auto V = static_cast<const __nv_bfloat16*>(v);
     auto O = static_cast<__nv_bfloat16*>(o);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(attn_small_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             int(size_t(kWarpsPerBlock) * 3 * kMaxL * 65 * sizeof(float)));
+        attr_done = true;
+    }
     if (D == 64) {
-        cudaFuncSetAttribute(attn_small_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         attn_small_fwd_kernel<64><<<grid, kWarpsPerBlock * 32, smem, st>>>(Q, K, V, O, a, nseq, heads, L, scale);
     } else {
         attn_small_fwd_kernel<32><<<grid, kWarpsPerBlock * 32, smem, st>>>(Q, K, V, O, a, nseq, heads, L, scale);
@@ -216,11 +221,17 @@ int t2v_attn_small_bwd(const void* q, const void* k, const void* v, const void* 
     auto B = [](const void* p) { return static_cast<const __nv_bfloat16*>(p); };
     auto W = [](void* p) { return static_cast<__nv_bfloat16*>(p); };
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(attn_small_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             int(size_t(kWarpsPerBlock) * 4 * kMaxL * 65 * sizeof(float)));
+        cudaFuncSetAttribute(attn_small_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             int(size_t(kWarpsPerBlock) * 4 * kMaxL * 33 * sizeof(float)));
+        attr_done = true;
+    }
     if (D == 64) {
-        cudaFuncSetAttribute(attn_small_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         attn_small_bwd_kernel<64><<<grid, kWarpsPerBlock * 32, smem, st>>>(B(q), B(k), B(v), B(dout), W(dq), W(dk), W(dv), a, nseq, heads, L, scale);
     } else {
-        cudaFuncSetAttribute(attn_small_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         attn_small_bwd_kernel<32><<<grid, kWarpsPerBlock * 32, smem, st>>>(B(q), B(k), B(v), B(dout), W(dq), W(dk), W(dv), a, nseq, heads, L, scale);
     }
     return launch_checked(int(cudaGetLastError()), "attn_small_bwd");

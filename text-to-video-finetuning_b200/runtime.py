@@ -1,0 +1,118 @@
+"""Step-level runtime: flat parameter arena (fp32 master / fp32 gradient / bf16 compute shadow), the single
+data-parallel gradient all-reduce, and CUDA-graph capture of the whole forward+backward.
+
+B200-first design notes
+  * 180 GB of HBM per GPU makes three flat copies of a 1.4 B-parameter model (5.6 + 5.6 + 2.8 GB) a non-issue, and a
+    flat layout turns per-step housekeeping into three kernels: one memset (zero grads), one cast (fp32 -> bf16 shadow
+    in kernel layout) and ONE ncclAllReduce over NVLink/NVSwitch for the gradients (the north-star's only collective;
+    the reference reaches NCCL implicitly through accelerate/DDP, train.py:661,861).
+  * A step has ~4-5 thousand kernel launches; replaying it as a CUDA graph removes the host launch cost entirely.
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops, prims
+
+
+def _align(n, a=64):
+    return (n + a - 1) // a * a
+
+
+class ParamArena:
+    """Adopts a module's parameters into flat buffers.  Parameters keep their identity, shape, strides and names;
+    only their storage moves.  `param.grad` becomes a view into the flat gradient buffer and matrix-like weights get a
+    `_t2v_shadow` bf16 view in kernel layout ([Cout, KH, KW, Cin] / [out, 1, 1, in])."""
+
+    def __init__(self, module, device=None):
+        params = [p for p in module.parameters()]
+        if not params:
+            raise ValueError("module has no parameters")
+        device = device or params[0].device
+        for p in params:
+            if p.dtype != torch.float32:
+                raise ValueError("ParamArena expects fp32 master parameters (the reference keeps the UNet in fp32 under autocast)")
+        # matrices first (they need a bf16 shadow), then vectors; trainable and frozen alike
+        mats = [p for p in params if p.dim() >= 2]
+        vecs = [p for p in params if p.dim() < 2]
+        self.params = mats + vecs
+        offs, off = [], 0
+        for p in self.params:
+            offs.append(off)
+            off += _align(p.numel())
+        self.total = off
+        self.n_mat = sum(_align(p.numel()) for p in mats)
+        self.master = torch.zeros(self.total, device=device, dtype=torch.float32)
+        self.grad = torch.zeros(self.total, device=device, dtype=torch.float32)
+        self.shadow = torch.zeros(max(self.n_mat, 8), device=device, dtype=torch.bfloat16)
+        with torch.no_grad():
+            for p, o in zip(self.params, offs):
+                n = p.numel()
+                src = p.detach().to(device)
+                phys = ops._phys(src) if p.dim() >= 2 else src
+                if not phys.is_contiguous():
+                    raise ValueError("conv weights must be in channels_last memory format before adoption")
+                self.master[o:o + n].copy_(phys.reshape(-1))
+                view = torch.as_strided(self.master, p.shape, p.stride(), o)
+                p.data = view
+                p.grad = torch.as_strided(self.grad, p.shape, p.stride(), o)
+                if p.dim() >= 2:
+                    p._t2v_shadow = self.shadow[o:o + n].view(ops._phys(view).shape)
+        self.offsets = offs
+        self.refresh_shadow()
+
+    def refresh_shadow(self):
+        """fp32 master -> bf16 compute copy for every matrix parameter: one kernel over the flat buffer."""
+        if self.n_mat:
+            prims.cast_f32_bf16(self.master[:self.n_mat], self.shadow[:self.n_mat])
+
+    def zero_grads(self):
+        self.grad.zero_()
+
+    def reattach_grads(self):
+        """optimizer.zero_grad(set_to_none=True) drops the views; put them back."""
+        for p, o in zip(self.params, self.offsets):
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
+                p.grad = torch.as_strided(self.grad, p.shape, p.stride(), o)
+
+    def grad_norm(self):
+        return self.grad.norm()
+
+
+def allreduce_gradients(arena, world_size=None, average=True):
+    """The one collective of the step: all-reduce the flat fp32 gradient buffer over NCCL (NVLink 5 / NVSwitch)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return None
+    world_size = world_size or dist.get_world_size()
+    if world_size == 1:
+        return None
+    if average:
+        arena.grad.div_(world_size)
+    return dist.all_reduce(arena.grad, op=dist.ReduceOp.SUM, async_op=False)
+
+
+class GraphedStep:
+    """Captures `fn(*static_inputs)` (forward + backward of one clip batch) into a CUDA graph and replays it.
+
+    `fn` must be free of host synchronisation and allocate only through PyTorch's caching allocator (true for every
+    Function in ops.py).  Inputs are copied into static buffers before each replay."""
+
+    def __init__(self, fn, example_inputs, warmup=2):
+        self.fn = fn
+        self.static_in = [x.clone() for x in example_inputs]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.static_out = fn(*self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_out = fn(*self.static_in)
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.static_in, inputs):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
