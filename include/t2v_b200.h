@@ -136,6 +136,11 @@ int t2v_scale_bf16(const void* a, void* out, int64_t n, float alpha, void* strea
 int t2v_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream);
 int t2v_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 
+/* nn.Dropout fused with the LoRA branch / TemporalConvLayer stage: out = base + scale * x * mask / (1 - p), mask drawn
+ * from a stateless counter-based generator keyed by (seed, element index); calling it again with the same seed on dy
+ * (base NULL) is the backward.  (reference utils/lora.py:57-62 dropout after lora_up; TemporalConvLayer Dropout(0.1))    */
+int t2v_dropout_scale_add(const void* x, const void* base, void* out, int64_t n, float p, float scale, uint64_t seed, void* stream);
+
 /* Upsample2D's F.interpolate(mode="nearest") on [N][H][W][C] and its gradient (any size ratio).                      */
 int t2v_upsample_nearest_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t Ho, int32_t Wo, int32_t C, void* stream);
 int t2v_upsample_nearest_bwd(const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t Ho, int32_t Wo, int32_t C, void* stream);

@@ -192,6 +192,29 @@ def scale_bf16(a, alpha):
     return (a.float() * alpha).to(BF)
 
 
+def _mix32(seed, idx):
+    """splitmix64 finaliser, bit-identical to mix32() in elementwise.cu (int64 arithmetic wraps like uint64)."""
+    def u64(v):
+        v &= 0xFFFFFFFFFFFFFFFF
+        return v - (1 << 64) if v >= (1 << 63) else v
+    z = idx * u64(0x9E3779B97F4A7C15) + u64(seed)
+    def lsr(v, s):
+        return (v >> s) & ((1 << (64 - s)) - 1)
+    z = (z ^ lsr(z, 30)) * u64(0xBF58476D1CE4E5B9)
+    z = (z ^ lsr(z, 27)) * u64(0x94D049BB133111EB)
+    return lsr(z ^ lsr(z, 31), 32)
+
+
+def dropout_scale_add(x, base, p, scale, seed):
+    idx = torch.arange(x.numel(), dtype=torch.int64, device=x.device)
+    keep = (_mix32(seed, idx) >= int(float(p) * 4294967296.0)).view(x.shape)
+    k = torch.tensor(scale, dtype=torch.float32) / (torch.tensor(1.0, dtype=torch.float32) - torch.tensor(p, dtype=torch.float32))
+    y = torch.where(keep, x.float() * k.to(x.device), torch.zeros((), device=x.device))
+    if base is not None:
+        y = y + base.float()
+    return y.to(BF)
+
+
 def add_f32(a, b):
     return a + b
 

@@ -9,6 +9,8 @@ if ROOT not in sys.path:
 
 
 def pytest_configure(config):
+    import torch
+    torch.set_num_threads(min(16, os.cpu_count() or 1))  # CPU oracle: avoid oversubscription when test processes run in parallel
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 

@@ -28,7 +28,7 @@ def main():
     def run(node):
         try:
             r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "--no-header", "-p", "no:cacheprovider", node],
-                               cwd=ROOT, capture_output=True, text=True, timeout=300)
+                               cwd=ROOT, capture_output=True, text=True, timeout=900)
             return node, r.returncode, (r.stdout + r.stderr)[-3000:]
         except subprocess.TimeoutExpired:
             return node, -9, "TIMEOUT"

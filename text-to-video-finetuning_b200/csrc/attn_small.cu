@@ -198,6 +198,8 @@ int t2v_attn_small_fwd(const void* q, const void* k, const void* v, void* o, int
     if (!attr_done) {
         cudaFuncSetAttribute(attn_small_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              int(size_t(kWarpsPerBlock) * 3 * kMaxL * 65 * sizeof(float)));
+        cudaFuncSetAttribute(attn_small_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             int(size_t(kWarpsPerBlock) * 3 * kMaxL * 33 * sizeof(float)));
         attr_done = true;
     }
     if (D == 64) {

@@ -278,7 +278,8 @@ __global__ void copy_cols_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfl
 
 // ------------------------------------------------------------------------------------------------ reductions
 // Segmented column sum: out[s][c] (+)= sum_p x[s][p][c].  Grid (chunks, S); per-thread 8-channel vectors.
-__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int64_t P, int C, int chunk_rows) {
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int64_t P, int C, int chunk_rows,
+                              int ld, int col0) {  // C = width of this column block, ld = full row length, col0 = first column
     extern __shared__ float sh[];  // [C]
     const int s = blockIdx.y;
     const int V = C >> 3;
@@ -289,10 +290,11 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __rest
     if (pl < lanes) {
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const int64_t p0 = int64_t(blockIdx.x) * chunk_rows, p1 = min(P, p0 + chunk_rows);
-        const uint4* xs = reinterpret_cast<const uint4*>(x + int64_t(s) * P * C) + cv;
+        const uint4* xs = reinterpret_cast<const uint4*>(x + int64_t(s) * P * ld + col0) + cv;
+        const int LV = ld >> 3;
         for (int64_t p = p0 + pl; p < p1; p += lanes) {
             float v[8];
-            unpack8e(__ldg(xs + p * V), v);
+            unpack8e(__ldg(xs + p * LV), v);
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] += v[j];
         }
@@ -300,7 +302,7 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __rest
         for (int j = 0; j < 8; ++j) atomicAdd(&sh[cv * 8 + j], acc[j]);
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(out + int64_t(s) * C + c, sh[c]);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(out + int64_t(s) * ld + col0 + c, sh[c]);
 }
 // out[c] += sum_s x[s][c] for a small fp32 matrix
 __global__ void colsum_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int S, int C) {
@@ -348,6 +350,31 @@ __global__ void softmax_bwd_kernel(const __nv_bfloat16* __restrict__ p, const fl
         __nv_bfloat16* o_ = ds + r * ld_p;
         for (int c = lane; c < ld_p; c += 32)
             o_[c] = __float2bfloat16_rn(c < n_valid ? __bfloat162float(pr[c]) * (dr[c] - dot) * scale : 0.f);
+    }
+}
+
+// out = base + scale * x * mask / (1 - p), mask ~ Bernoulli(1 - p) from a counter-based generator keyed by
+// (seed, element index): the backward pass regenerates the same mask instead of storing it.
+__device__ __forceinline__ uint32_t mix32(uint64_t seed, uint64_t idx) {
+    uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull;  // splitmix64 finaliser: counter-based, stateless
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return uint32_t((z ^ (z >> 31)) >> 32);
+}
+__global__ void dropout_scale_add_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ base,
+                                         __nv_bfloat16* __restrict__ out, int64_t nvec, float p, float scale, uint64_t seed) {
+    const uint32_t thresh = uint32_t(double(p) * 4294967296.0);
+    const float k = scale / (1.f - p);
+    GRID_STRIDE(i, nvec) {
+        float v[8], b[8];
+        unpack8e(__ldg(reinterpret_cast<const uint4*>(x) + i), v);
+        if (base) unpack8e(__ldg(reinterpret_cast<const uint4*>(base) + i), b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool keep = mix32(seed, uint64_t(i) * 8 + j) >= thresh;
+            v[j] = (keep ? v[j] * k : 0.f) + (base ? b[j] : 0.f);
+        }
+        reinterpret_cast<uint4*>(out)[i] = pack8e(v);
     }
 }
 
@@ -452,14 +479,17 @@ int t2v_copy_cols(const void* src, void* dst, int64_t M, int32_t C, int32_t src_
     return launch_checked(int(cudaGetLastError()), "copy_cols");
 }
 int t2v_colsum(const void* x, float* out, int32_t S, int64_t P, int32_t C, void* stream) {
-    if (C % 8 || C / 8 > 1024) return fail(-2, "colsum: C=%d unsupported", C);
-    const int V = C / 8;
-    int bs = 256;
-    while (bs < V) bs += 32;
+    if (C % 8) return fail(-2, "colsum: C=%d must be a multiple of 8", C);
     const int64_t want = std::max<int64_t>(1, (4 * 148 + S - 1) / S);
     const int chunk = int(std::min<int64_t>(P, std::max<int64_t>(16, (P + want - 1) / want)));
     const int chunks = int((P + chunk - 1) / chunk);
-    colsum_kernel<<<dim3(chunks, S), bs, C * sizeof(float), ST>>>(BF(x), out, P, C, chunk);
+    for (int col0 = 0; col0 < C; col0 += 4096) {  // column blocks of <= 4096 channels (512 vectors per block row)
+        const int cw = std::min(4096, C - col0);
+        int bs = 256;
+        while (bs < cw / 8) bs += 32;
+        colsum_kernel<<<dim3(chunks, S), bs, cw * sizeof(float), ST>>>(BF(x), out, P, cw, chunk, C, col0);
+        if (col0) count_launch();
+    }
     return launch_checked(int(cudaGetLastError()), "colsum");
 }
 int t2v_colsum_f32(const float* x, float* out, int32_t S, int32_t C, void* stream) {
@@ -476,6 +506,12 @@ int t2v_softmax_bwd(const void* p, const float* dp, void* ds, int64_t rows, int3
     const int grid = int(std::min<int64_t>((rows + 7) / 8, 148 * 16));
     softmax_bwd_kernel<<<grid, 256, 0, ST>>>(BF(p), dp, BFW(ds), rows, n_valid, ld_p, ld_dp, scale);
     return launch_checked(int(cudaGetLastError()), "softmax_bwd");
+}
+int t2v_dropout_scale_add(const void* x, const void* base, void* out, int64_t n, float p, float scale, uint64_t seed, void* stream) {
+    if (n % 8) return fail(-2, "dropout_scale_add: n must be a multiple of 8");
+    if (!(p >= 0.f && p < 1.f)) return fail(-2, "dropout_scale_add: p=%f out of range", p);
+    dropout_scale_add_kernel<<<ew_grid(n / 8), 256, 0, ST>>>(BF(x), BF(base), BFW(out), n / 8, p, scale, seed);
+    return launch_checked(int(cudaGetLastError()), "dropout_scale_add");
 }
 int t2v_timestep_embedding(const int64_t* t, void* out, int32_t B, int32_t dim, void* stream) {
     timestep_embed_kernel<<<ew_grid(int64_t(B) * dim / 2), 256, 0, ST>>>(t, BFW(out), B, dim);

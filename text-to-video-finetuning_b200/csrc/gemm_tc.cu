@@ -309,6 +309,13 @@ int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
                      const uint32_t* box, const uint32_t* elem_strides) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return -1;
+    // cuTensorMapEncodeTiled is a driver-API call: it needs a context bound to the calling thread.  Autograd worker
+    // threads may reach this point before any runtime-API call has bound the primary context, so bind it once.
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) {
+        cudaFree(nullptr);
+        ctx_bound = true;
+    }
     cuuint64_t gdim[5], gstr[4];
     cuuint32_t bdim[5], estr[5];
     for (int i = 0; i < rank; ++i) {

@@ -156,12 +156,11 @@ class TemporalConvLayer(nn.Module):
     def forward(self, x, num_frames=1):
         N, H, W, C = x.shape
         B = N // num_frames
-        for seq in (self.conv2, self.conv3, self.conv4):
-            if self.training and seq[2].p > 0:
-                raise NotImplementedError("TemporalConvLayer dropout > 0 in training mode: use eval_train / p=0 (round 1)")
         identity, h = ops.fork(x)
         for i, seq in enumerate((self.conv1, self.conv2, self.conv3, self.conv4)):
             h = run_group_norm(seq[0], h, True, B)
+            if i > 0 and self.training and seq[2].p > 0:  # nn.Dropout between SiLU and the conv (own RNG stream)
+                h = ops.dropout(h, seq[2].p)
             h = h.view(B, num_frames, H * W, h.shape[-1])
             res = identity.view(B, num_frames, H * W, C) if i == 3 else None
             h = run_conv(seq[-1], h, residual=res, pads=(1, 1, 0, 0))

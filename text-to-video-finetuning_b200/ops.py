@@ -112,6 +112,8 @@ class _Conv(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, rowbias, residual, stride, pads, rb_div, out_fp32, cin_pad, cout_pad, alpha):
         w = weight_bf16(weight)
+        cin_pad = x.shape[-1] - w.shape[-1]        # boundary tensors arrive zero-padded to 8 channels
+        cout_pad = (-w.shape[0]) % 8                # ... and leave padded to a multiple of 8
         if cin_pad or cout_pad:  # 3/4-channel boundary tensors are padded to 8 channels (TMA rows are >= 16 bytes)
             Co, KH, KW, Ci = w.shape
             wp = torch.zeros((Co + cout_pad, KH, KW, Ci + cin_pad), device=w.device, dtype=w.dtype)
@@ -150,6 +152,8 @@ class _Conv(Function):
                 tmp = torch.zeros(Co, device=dy.device, dtype=torch.float32)
                 prims.colsum(dy, tmp.view(1, Co), 1, N * Ho * Wo, Co)
                 gb += tmp[:Co - cout_pad]
+                if d_rowbias is not None:
+                    d_rowbias = d_rowbias[:, :Co - cout_pad].contiguous()
             elif d_rowbias is not None:
                 prims.colsum_f32(d_rowbias, gb)
             else:
@@ -262,6 +266,38 @@ class _Silu(Function):
 
 def silu(x):
     return _Silu.apply(x)
+
+
+class _DropoutScaleAdd(Function):
+    """base + scale * dropout_p(x) with a regenerated (not stored) mask."""
+
+    @staticmethod
+    def forward(ctx, x, base, p, scale, seed):
+        ctx.meta = (p, scale, seed, base is not None)
+        return prims.dropout_scale_add(x, base, p, scale, seed)
+
+    @staticmethod
+    def backward(ctx, dy):
+        p, scale, seed, has_base = ctx.meta
+        dy = _cont(dy)
+        return prims.dropout_scale_add(dy, None, p, scale, seed), (dy if has_base else None), None, None, None
+
+
+_dropout_counter = [0]
+
+
+def next_dropout_seed():
+    """Seeds follow torch's global seed so runs are reproducible; each call site/step gets a fresh stream."""
+    _dropout_counter[0] += 1
+    return (torch.initial_seed() * 1000003 + _dropout_counter[0]) & 0x7FFFFFFFFFFFFFFF
+
+
+def dropout_scale_add(x, base, p, scale=1.0, seed=None):
+    return _DropoutScaleAdd.apply(x, base, float(p), float(scale), next_dropout_seed() if seed is None else seed)
+
+
+def dropout(x, p, seed=None):
+    return _DropoutScaleAdd.apply(x, None, float(p), 1.0, next_dropout_seed() if seed is None else seed)
 
 
 # ---------------------------------------------------------------------------------------------------- resampling / concat

@@ -195,6 +195,14 @@ def scale_bf16(a, alpha):
     return out
 
 
+def dropout_scale_add(x, base, p, scale, seed):
+    """base + scale * dropout_p(x); the mask is a pure function of (seed, element index)."""
+    _chk_bf16(x, base)
+    out = torch.empty_like(x)
+    native.check(native.lib().t2v_dropout_scale_add(_p(x), _p(base), _p(out), x.numel(), float(p), float(scale), int(seed), _stream()))
+    return out
+
+
 def add_f32(a, b):
     _chk_f32(a, b)
     out = torch.empty_like(a)

@@ -1,0 +1,294 @@
+"""`python train.py --config cfg.yaml` - the reference's training entry point on the B200-native hot path.
+
+`main(**yaml)` accepts the same keyword surface as the reference's `train.py:457-514`, so the v2 YAML configs load
+unchanged (keys this build does not act on - validation sampling, webui export, trackers - are accepted and ignored).
+What this file owns is the *step*: parameter selection (`handle_trainable_modules`, :316-337), LoRA injection through
+`LoraHandler` (:557-572), optimizer parameter groups (`create_optimizer_params`, :205-236), and per optimisation step:
+noise + timestep sampling (:751-757), the fused add_noise -> UNet fwd+bwd -> MSE step (`step.DataParallelStep`, two
+passes per video step like :814-834), ONE gradient all-reduce across ranks, clipping, AdamW, LR schedule, LoRA / UNet
+checkpoints.  One process per GPU (`torchrun --nproc-per-node N train.py --config ...`); no accelerate.
+
+Data: the hot path consumes latents.  Supported sources are the reference's latent cache (`cached_latent_dir` with
+`cached_{i}.pt` dicts written by `handle_cache_latents`, train.py:266-314) and `dataset_types: ['synthetic']`;
+raw-video datasets need decord and the VAE/text encoder (SURVEY section 8(f) 'next' rows) and raise a clear error.
+"""
+import argparse
+import itertools
+import math
+import os
+import time
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .models.unet_3d_condition import UNet3DConditionModel
+from .step import DataParallelStep, ddpm_alphas_cumprod, sample_noise
+from .utils.lora_handler import LORA_VERSIONS, LoraHandler
+
+already_printed_trainables = False
+
+
+def handle_trainable_modules(model, trainable_modules=None, is_enabled=True, negation=None):
+    """requires_grad by name-substring match; 'all' unlocks everything; LoRA params are never touched here."""
+    global already_printed_trainables
+    if trainable_modules is None:
+        return
+    count = 0
+    if any(name == "all" for name in trainable_modules):
+        model.requires_grad_(True)
+        count = len(list(model.parameters()))
+    else:
+        model.requires_grad_(False)
+        for name, param in model.named_parameters():
+            if "lora" not in name and any(tm in name for tm in trainable_modules):
+                param.requires_grad_(is_enabled)
+                count += 1
+    if count > 0 and not already_printed_trainables:
+        already_printed_trainables = True
+        print(f"{count} params have been processed.")
+
+
+def param_optim(model, condition, extra_params=None, is_lora=False, negation=None):
+    extra_params = extra_params if extra_params and len(extra_params.keys()) > 0 else None
+    return {"model": model, "condition": condition, "extra_params": extra_params, "is_lora": is_lora, "negation": negation}
+
+
+def _group(name=None, param=None, lr=None, extra=None, params=None):
+    g = {"params": params} if params is not None else {"name": name, "params": param, "lr": lr}
+    if extra:
+        g.update(extra)
+    return g
+
+
+def create_optimizer_params(model_list, lr):
+    groups = []
+    for spec in model_list:
+        model, condition, extra, is_lora, _ = spec.values()
+        if not condition:
+            continue
+        if is_lora and isinstance(model, list):  # list of parameter iterators from the injector
+            groups.append(_group(params=itertools.chain(*model), extra=extra))
+        elif is_lora:
+            groups += [_group(n, p, lr, extra) for n, p in model.named_parameters() if "lora" in n]
+        else:
+            groups += [_group(n, p, lr, extra) for n, p in model.named_parameters() if "lora" not in n]
+    return groups
+
+
+def _lr_lambda(kind, warmup, total):
+    def f(step):
+        if step < warmup:
+            return float(step) / max(1, warmup)
+        if kind == "constant" or kind == "constant_with_warmup":
+            return 1.0
+        prog = (step - warmup) / max(1, total - warmup)
+        if kind == "linear":
+            return max(0.0, 1.0 - prog)
+        if kind == "cosine":
+            return 0.5 * (1.0 + math.cos(math.pi * min(1.0, prog)))
+        raise ValueError(f"unknown lr_scheduler {kind!r}")
+    return f
+
+
+class CachedLatents(torch.utils.data.Dataset):
+    """The reference's latent cache: cached_{i}.pt = {pixel_values: latents (4,F,h,w), prompt_ids, text_prompt, ...}
+    (train.py:266-314, utils/dataset.py:589-603) plus an optional precomputed 'text_embeds' (77, 1024) entry."""
+
+    def __init__(self, cache_dir):
+        self.files = sorted(os.path.join(cache_dir, f) for f in os.listdir(cache_dir) if f.endswith(".pt"))
+        if not self.files:
+            raise FileNotFoundError(f"no cached_*.pt latents under {cache_dir}")
+
+    def __len__(self):
+        return len(self.files)
+
+    def __getitem__(self, i):
+        return torch.load(self.files[i], map_location="cpu")
+
+
+class SyntheticLatents(torch.utils.data.Dataset):
+    def __init__(self, n=64, frames=16, hw=(32, 32), text_len=77, text_dim=1024, seed=0):
+        self.n, self.shape, self.tshape, self.seed = n, (4, frames, hw[0], hw[1]), (text_len, text_dim), seed
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        g = torch.Generator().manual_seed(self.seed * 100003 + i)
+        return {"pixel_values": torch.randn(self.shape, generator=g) * 0.18215, "text_embeds": torch.randn(self.tshape, generator=g)}
+
+
+def main(
+    pretrained_model_path: str,
+    output_dir: str,
+    train_data: Dict = None,
+    validation_data: Dict = None,
+    extra_train_data: list = [],
+    dataset_types: Tuple[str] = ("json",),
+    shuffle: bool = True,
+    validation_steps: int = 100,
+    trainable_modules: Tuple[str] = None,
+    trainable_text_modules: Tuple[str] = None,
+    extra_unet_params=None,
+    extra_text_encoder_params=None,
+    train_batch_size: int = 1,
+    max_train_steps: int = 500,
+    learning_rate: float = 5e-5,
+    scale_lr: bool = False,
+    lr_scheduler: str = "constant",
+    lr_warmup_steps: int = 0,
+    adam_beta1: float = 0.9,
+    adam_beta2: float = 0.999,
+    adam_weight_decay: float = 1e-2,
+    adam_epsilon: float = 1e-08,
+    max_grad_norm: float = 1.0,
+    gradient_accumulation_steps: int = 1,
+    gradient_checkpointing: bool = False,
+    text_encoder_gradient_checkpointing: bool = False,
+    checkpointing_steps: int = 500,
+    resume_from_checkpoint: Optional[str] = None,
+    resume_step: Optional[int] = None,
+    mixed_precision: Optional[str] = "fp16",
+    use_8bit_adam: bool = False,
+    enable_xformers_memory_efficient_attention: bool = True,
+    enable_torch_2_attn: bool = False,
+    seed: Optional[int] = None,
+    train_text_encoder: bool = False,
+    use_offset_noise: bool = False,
+    rescale_schedule: bool = False,
+    offset_noise_strength: float = 0.1,
+    extend_dataset: bool = False,
+    cache_latents: bool = False,
+    cached_latent_dir=None,
+    lora_version: str = LORA_VERSIONS[0],
+    save_lora_for_webui: bool = False,
+    only_lora_for_webui: bool = False,
+    lora_bias: str = "none",
+    use_unet_lora: bool = False,
+    use_text_lora: bool = False,
+    unet_lora_modules: Tuple[str] = ("ResnetBlock2D",),
+    text_encoder_lora_modules: Tuple[str] = ("CLIPEncoderLayer",),
+    save_pretrained_model: bool = True,
+    lora_rank: int = 16,
+    lora_path: str = "",
+    lora_unet_dropout: float = 0.1,
+    lora_text_dropout: float = 0.1,
+    logger_type: str = "tensorboard",
+    **kwargs,
+):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if train_text_encoder or use_text_lora:
+        raise NotImplementedError("text-encoder training is outside the B200 hot path of this build (SURVEY 8(f) row 2)")
+    if use_8bit_adam:
+        raise NotImplementedError("bitsandbytes 8-bit Adam is not available; fused AdamW is SURVEY 8(f) row 1")
+    if seed is not None:
+        torch.manual_seed(seed + rank)
+    if rank == 0:
+        os.makedirs(output_dir, exist_ok=True)
+
+    unet = UNet3DConditionModel.from_pretrained(pretrained_model_path, subfolder="unet")
+    unet.requires_grad_(False)
+    if scale_lr:
+        learning_rate = learning_rate * gradient_accumulation_steps * train_batch_size * world
+
+    lora_manager = LoraHandler(version=lora_version, use_unet_lora=use_unet_lora, use_text_lora=False,
+                               save_for_webui=save_lora_for_webui, only_for_webui=only_lora_for_webui,
+                               unet_replace_modules=list(unet_lora_modules),
+                               text_encoder_replace_modules=list(text_encoder_lora_modules), lora_bias=lora_bias)
+    unet_lora_params, unet_negation = lora_manager.add_lora_to_model(use_unet_lora, unet, lora_manager.unet_replace_modules,
+                                                                     lora_unet_dropout, lora_path, r=lora_rank)
+    unet = unet.to(dev)
+    unet.train()
+    if kwargs.get("eval_train", False):  # train.py:779-781
+        unet.eval()
+    handle_trainable_modules(unet, trainable_modules, is_enabled=True, negation=unet_negation)
+    unet._set_gradient_checkpointing(gradient_checkpointing)
+
+    extra_unet_params = extra_unet_params or {}
+    groups = create_optimizer_params([
+        param_optim(unet, trainable_modules is not None, extra_params=extra_unet_params, negation=unet_negation),
+        param_optim(unet_lora_params, use_unet_lora, is_lora=True, extra_params={**{"lr": learning_rate}, **extra_unet_params}),
+    ], learning_rate)
+
+    abar = ddpm_alphas_cumprod(device=dev)
+    stepper = DataParallelStep(unet, abar, passes=2, use_graph=False)  # parameters now live in the flat arena
+    optimizer = torch.optim.AdamW(groups, lr=learning_rate, betas=(adam_beta1, adam_beta2), weight_decay=adam_weight_decay, eps=adam_epsilon)
+    sched = torch.optim.lr_scheduler.LambdaLR(optimizer, _lr_lambda(lr_scheduler, lr_warmup_steps * gradient_accumulation_steps,
+                                                                    max_train_steps * gradient_accumulation_steps))
+
+    kinds = [dataset_types] if isinstance(dataset_types, str) else list(dataset_types)
+    if cached_latent_dir:
+        dataset = CachedLatents(cached_latent_dir)
+    elif "synthetic" in kinds:
+        td = train_data or {}
+        dataset = SyntheticLatents(n=td.get("n", 64), frames=td.get("n_sample_frames", 16),
+                                   hw=(td.get("height", 256) // 8, td.get("width", 256) // 8))
+    else:
+        raise NotImplementedError(f"dataset_types={kinds}: raw-video datasets need decord + VAE/text encoders (SURVEY 8(f)); "
+                                  "use cached_latent_dir or dataset_types: ['synthetic']")
+    sampler = torch.utils.data.distributed.DistributedSampler(dataset, world, rank, shuffle=shuffle) if world > 1 else None
+    loader = torch.utils.data.DataLoader(dataset, batch_size=train_batch_size, shuffle=shuffle and sampler is None, sampler=sampler)
+
+    global_step, micro = 0, 0
+    t0 = time.time()
+    while global_step < max_train_steps:
+        for batch in loader:
+            latents = batch["pixel_values"].to(dev, torch.float32)
+            if "text_embeds" not in batch:
+                raise NotImplementedError("batch has no 'text_embeds': the frozen text encoder is a SURVEY 8(f) 'next' row")
+            text = batch["text_embeds"].to(dev, torch.float32)
+            noise = sample_noise(latents, offset_noise_strength, use_offset_noise and not rescale_schedule)
+            timesteps = torch.randint(0, abar.shape[0], (latents.shape[0],), device=dev, dtype=torch.int64)
+            if latents.shape[2] <= 1:
+                stepper.passes = 1  # single-frame data breaks out after the first pass (train.py:832)
+            loss = stepper(latents, noise, timesteps, text)
+            micro += 1
+            if micro % gradient_accumulation_steps:
+                continue  # gradients keep accumulating in the flat buffer
+            if max_grad_norm is not None:
+                torch.nn.utils.clip_grad_norm_([p for g in optimizer.param_groups for p in g["params"]], max_grad_norm)
+            optimizer.step()
+            sched.step()
+            global_step += 1
+            if rank == 0 and (global_step % 10 == 0 or global_step == 1):
+                print(f"step {global_step}/{max_train_steps} loss {loss.item():.5f} ({(time.time() - t0) / global_step:.3f} s/step)")
+            if rank == 0 and global_step % checkpointing_steps == 0:
+                save_checkpoint(unet, lora_manager, output_dir, global_step, use_unet_lora, save_pretrained_model)
+            if global_step >= max_train_steps:
+                break
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        save_checkpoint(unet, lora_manager, output_dir, global_step, use_unet_lora, save_pretrained_model, final=True)
+
+
+def save_checkpoint(unet, lora_manager, output_dir, step, use_unet_lora, save_pretrained_model, final=False):
+    """LoRA in the cloneofsimo list format (`lora/<step>_unet.pt`), UNet in diffusers layout (`unet/`)."""
+    path = output_dir if final else os.path.join(output_dir, f"checkpoint-{step}")
+    os.makedirs(path, exist_ok=True)
+    if use_unet_lora:
+        from .utils.lora import save_lora_weight
+        os.makedirs(os.path.join(path, "lora"), exist_ok=True)
+        save_lora_weight(unet, os.path.join(path, "lora", f"{step}_unet.pt"), lora_manager.unet_replace_modules)
+    elif save_pretrained_model:
+        unet.save_pretrained(os.path.join(path, "unet"))
+
+
+def load_config(path):
+    import yaml
+    with open(path) as f:
+        return yaml.safe_load(f)
+
+
+if __name__ == "__main__":
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--config", type=str, default="./configs/v2/train_config.yaml")
+    main(**load_config(parser.parse_args().config))
