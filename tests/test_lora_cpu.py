@@ -94,6 +94,7 @@ def test_zero_init_identity_and_collapse_round_trip():
     m, _ = _model()
     with _quiet():
         params, names = mylora.inject_trainable_lora_extended(m, mylora.UNET_EXTENDED_TARGET_REPLACE, r=8)
+    m.eval()  # freshly injected wrappers default to train mode (live dropout), exactly as in the reference
     assert params and all("lora" not in n for n in sd)
     x, t, ehs = torch.randn(1, 4, 2, 8, 8), torch.tensor([500]), torch.randn(1, 7, 64)
     with emulated_prims():
