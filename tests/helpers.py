@@ -22,21 +22,20 @@ def emulated_prims():
 
 
 def seeded_state_dict(model, seed=0, conv4_std=0.02):
-    """Deterministic weights for parity tests: module defaults under a fixed seed, with the zero-initialised
-    TemporalConvLayer.conv4 re-drawn N(0, std) so the temporal-conv branch carries signal."""
-    g = torch.Generator().manual_seed(seed)
+    """Deterministic weights for parity tests, independent of module declaration order (each tensor is drawn from a
+    generator seeded by crc32(key) ^ seed).  Norm scales ~ 1 + 0.1 N, biases ~ 0.05 N, matrices ~ N / sqrt(fan_in);
+    the zero-initialised TemporalConvLayer.conv4 is re-drawn N(0, std) so the temporal-conv branch carries signal."""
+    import zlib
     sd = {}
     for k, v in model.state_dict().items():
+        g = torch.Generator().manual_seed((zlib.crc32(k.encode()) ^ (seed * 2654435761)) & 0x7FFFFFFF)
+        shape = tuple(v.shape)
         if ".conv4.3." in k:
-            sd[k] = torch.randn(v.shape, generator=g) * conv4_std
+            sd[k] = torch.randn(shape, generator=g) * conv4_std
         elif v.dim() <= 1:
-            if k.endswith("weight"):
-                sd[k] = 1.0 + 0.1 * torch.randn(v.shape, generator=g)   # norm scales
-            else:
-                sd[k] = 0.05 * torch.randn(v.shape, generator=g)        # biases / norm shifts
+            sd[k] = 1.0 + 0.1 * torch.randn(shape, generator=g) if k.endswith("weight") else 0.05 * torch.randn(shape, generator=g)
         else:
-            fan_in = v[0].numel()
-            sd[k] = torch.randn(v.shape, generator=g) / fan_in ** 0.5
+            sd[k] = torch.randn(shape, generator=g) / (v[0].numel() ** 0.5)
     return sd
 
 
