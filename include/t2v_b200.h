@@ -122,6 +122,10 @@ int t2v_nhwc8_to_latents(const void* in, float* out, int32_t B, int32_t C, int32
 int t2v_mse_loss(const void* pred, const float* target, float* loss, const float* gout, void* dpred, int32_t B, int32_t C,
                  int32_t F, int32_t HW, void* stream);
 
+/* AutoencoderKL latent_dist.sample() + rearrange + * scale (train.py:343-345): moments [B*F][HW][8] bf16 (mean | logvar),
+ * eps (B,4,F,HW) fp32 -> out (B,4,F,HW) fp32 = (mean + exp(0.5 clamp(logvar,-30,20)) eps) * scale.                    */
+int t2v_vae_sample(const void* moments, const float* eps, float* out, int32_t B, int32_t F, int32_t HW, float scale, void* stream);
+
 /* GEGLU (diffusers FeedForward.net[0]): proj [M][2I] -> out [M][I] = h * gelu_erf(gate).                           */
 int t2v_geglu_fwd(const void* proj, void* out, int64_t M, int32_t I, void* stream);
 int t2v_geglu_bwd(const void* proj, const void* dout, void* dproj, int64_t M, int32_t I, void* stream);

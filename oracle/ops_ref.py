@@ -321,6 +321,13 @@ def nhwc8_to_latents(x, B, C, Fr):
     return x.float().view(B, Fr, H, W, 8)[..., :C].permute(0, 4, 1, 2, 3).contiguous()
 
 
+def vae_sample(moments, eps, B, Fr, scale):
+    _, h, w, _ = moments.shape
+    m = moments.float().view(B, Fr, h, w, 8)
+    mean, logvar = m[..., :4].permute(0, 4, 1, 2, 3), m[..., 4:].permute(0, 4, 1, 2, 3).clamp(-30.0, 20.0)
+    return ((mean + torch.exp(0.5 * logvar) * eps) * scale).contiguous()
+
+
 def mse_loss_fwd(pred, target):
     B, C, Fr, H, W = target.shape
     p = nhwc8_to_latents(pred, B, C, Fr)

@@ -142,10 +142,10 @@ def finetune_loss(p, cfg, latents, noise, timesteps, encoder_hidden_states, alph
     return loss, pred
 
 
-def tensor_to_vae_latent(p_vae, pixels, eps_noise):
+def tensor_to_vae_latent(p_vae, pixels, eps_noise, block_out_channels=(128, 256, 512, 512), layers_per_block=2):
     """train.py:339-347: (B, F, 3, H, W) pixels -> (B, 4, F, H/8, W/8) latents * 0.18215 (hard-coded, H9)."""
     B, nf = pixels.shape[:2]
     flat = pixels.reshape((B * nf,) + tuple(pixels.shape[2:]))
-    lat = L.diagonal_gaussian_sample(L.vae_encode_moments(p_vae, flat), eps_noise)
+    lat = L.diagonal_gaussian_sample(L.vae_encode_moments(p_vae, flat, block_out_channels, layers_per_block), eps_noise)
     lat = lat.reshape((B, nf) + tuple(lat.shape[1:])).permute(0, 2, 1, 3, 4)
     return lat * 0.18215

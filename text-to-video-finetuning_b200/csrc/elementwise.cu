@@ -378,6 +378,26 @@ __global__ void dropout_scale_add_kernel(const __nv_bfloat16* __restrict__ x, co
     }
 }
 
+// DiagonalGaussianDistribution.sample() fused with tensor_to_vae_latent's rearrange and * 0.18215 (train.py:343-345):
+// moments [B*F][HW][8] bf16 (mean = ch 0..3, logvar = ch 4..7)  ->  latents (B, 4, F, HW) fp32
+__global__ void vae_sample_kernel(const __nv_bfloat16* __restrict__ mom, const float* __restrict__ eps, float* __restrict__ out,
+                                  int B, int F, int HW, float scale) {
+    const int64_t npix = int64_t(B) * F * HW;
+    GRID_STRIDE(i, npix) {
+        const int hw = int(i % HW);
+        const int f = int((i / HW) % F);
+        const int b = int(i / (int64_t(HW) * F));
+        float v[8];
+        unpack8e(__ldg(reinterpret_cast<const uint4*>(mom) + i), v);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int64_t o = ((int64_t(b) * 4 + c) * F + f) * HW + hw;
+            const float lv = fminf(fmaxf(v[4 + c], -30.f), 20.f);
+            out[o] = (v[c] + expf(0.5f * lv) * eps[o]) * scale;
+        }
+    }
+}
+
 // Timesteps(dim, flip_sin_to_cos=True, shift=0): [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(10000) i / half)  -> bf16 [B][dim]
 __global__ void timestep_embed_kernel(const int64_t* __restrict__ t, __nv_bfloat16* __restrict__ out, int B, int dim) {
     const int half = dim >> 1;
@@ -512,6 +532,10 @@ int t2v_dropout_scale_add(const void* x, const void* base, void* out, int64_t n,
     if (!(p >= 0.f && p < 1.f)) return fail(-2, "dropout_scale_add: p=%f out of range", p);
     dropout_scale_add_kernel<<<ew_grid(n / 8), 256, 0, ST>>>(BF(x), BF(base), BFW(out), n / 8, p, scale, seed);
     return launch_checked(int(cudaGetLastError()), "dropout_scale_add");
+}
+int t2v_vae_sample(const void* moments, const float* eps, float* out, int32_t B, int32_t F, int32_t HW, float scale, void* stream) {
+    vae_sample_kernel<<<ew_grid(int64_t(B) * F * HW), 256, 0, ST>>>(BF(moments), eps, out, B, F, HW, scale);
+    return launch_checked(int(cudaGetLastError()), "vae_sample");
 }
 int t2v_timestep_embedding(const int64_t* t, void* out, int32_t B, int32_t dim, void* stream) {
     timestep_embed_kernel<<<ew_grid(int64_t(B) * dim / 2), 256, 0, ST>>>(t, BFW(out), B, dim);

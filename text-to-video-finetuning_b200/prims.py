@@ -331,6 +331,16 @@ def nhwc8_to_latents(x, B, C, F):
     return out
 
 
+def vae_sample(moments, eps, B, F, scale):
+    """moments [B*F,h,w,8] bf16, eps (B,4,F,h,w) fp32 -> latents (B,4,F,h,w) fp32."""
+    _chk_bf16(moments)
+    _chk_f32(eps)
+    _, h, w, _ = moments.shape
+    out = torch.empty((B, 4, F, h, w), device=moments.device, dtype=torch.float32)
+    native.check(native.lib().t2v_vae_sample(_p(moments), _p(eps), _p(out), B, F, h * w, float(scale), _stream()))
+    return out
+
+
 def mse_loss_fwd(pred, target):
     _chk_bf16(pred)
     _chk_f32(target)
