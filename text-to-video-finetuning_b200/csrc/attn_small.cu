@@ -48,11 +48,13 @@ __global__ void attn_small_fwd_kernel(const __nv_bfloat16* __restrict__ q, const
                                       int heads, int L, float scale) {
     extern __shared__ float sm_all[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* sq = sm_all + warp * 3 * kMaxL * (D + 1);
-    float* sk = sq + kMaxL * (D + 1);
-    float* sv = sk + kMaxL * (D + 1);
+    const int tile = L * (D + 1);  // shared memory is sized by the actual sequence length (occupancy)
+    float* sq = sm_all + warp * 3 * tile;
+    float* sk = sq + tile;
+    float* sv = sk + tile;
+    const int nwarps = blockDim.x >> 5;
     const int64_t total = nseq * heads;
-    for (int64_t w = blockIdx.x * int64_t(kWarpsPerBlock) + warp; w < total; w += int64_t(gridDim.x) * kWarpsPerBlock) {
+    for (int64_t w = blockIdx.x * int64_t(nwarps) + warp; w < total; w += int64_t(gridDim.x) * nwarps) {
         const int64_t z = w / heads;
         const int h = int(w % heads);
         const int64_t base = seq_base(a, z, h, D);
@@ -92,6 +94,8 @@ __global__ void attn_small_fwd_kernel(const __nv_bfloat16* __restrict__ q, const
     }
 }
 
+// Backward.  Phase 1 (lane j <-> key j): recompute P and dS row by row into shared memory.  Phase 2 (lane <-> head
+// dims lane, lane+32): dQ = dS K, dK = dS^T Q, dV = P^T dO as L x L register-light loops over broadcast scalars.
 template <int D>
 __global__ void attn_small_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                                       const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ dout,
@@ -99,12 +103,16 @@ __global__ void attn_small_bwd_kernel(const __nv_bfloat16* __restrict__ q, const
                                       SeqAddr a, int64_t nseq, int heads, int L, float scale) {
     extern __shared__ float sm_all[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* sq = sm_all + warp * 4 * kMaxL * (D + 1);
-    float* sk = sq + kMaxL * (D + 1);
-    float* sv = sk + kMaxL * (D + 1);
-    float* sd = sv + kMaxL * (D + 1);
+    const int tile = L * (D + 1);
+    float* sq = sm_all + warp * (4 * tile + 2 * L * L);
+    float* sk = sq + tile;
+    float* sv = sk + tile;
+    float* sd = sv + tile;
+    float* sp = sd + tile;      // P  [L][L]
+    float* ss = sp + L * L;     // dS [L][L] (already multiplied by the softmax scale)
+    const int nwarps = blockDim.x >> 5;
     const int64_t total = nseq * heads;
-    for (int64_t w = blockIdx.x * int64_t(kWarpsPerBlock) + warp; w < total; w += int64_t(gridDim.x) * kWarpsPerBlock) {
+    for (int64_t w = blockIdx.x * int64_t(nwarps) + warp; w < total; w += int64_t(gridDim.x) * nwarps) {
         const int64_t z = w / heads;
         const int h = int(w % heads);
         const int64_t base = seq_base(a, z, h, D);
@@ -114,10 +122,6 @@ __global__ void attn_small_bwd_kernel(const __nv_bfloat16* __restrict__ q, const
         load_tile<D>(v, base, a.seq_stride, L, sv, lane);
         load_tile<D>(dout, base, a.seq_stride, L, sd, lane);
         __syncwarp();
-        // lane j accumulates dK_j and dV_j rows in registers (D values each)
-        float dkj[D], dvj[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) dkj[d] = dvj[d] = 0.f;
         for (int i = 0; i < L; ++i) {
             float s = -INFINITY, dp = 0.f;
             if (lane < L) {
@@ -141,34 +145,32 @@ __global__ void attn_small_bwd_kernel(const __nv_bfloat16* __restrict__ q, const
             float dot = p * dp;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
-            const float ds = p * (dp - dot) * scale;  // dS_ij (already times the softmax scale)
             if (lane < L) {
+                sp[i * L + lane] = p;
+                ss[i * L + lane] = p * (dp - dot) * scale;
+            }
+        }
+        __syncwarp();
+        for (int i = 0; i < L; ++i) {
+            float aq[D / 32], ak[D / 32], av[D / 32];
 #pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    dkj[d] += ds * sq[i * (D + 1) + d];
-                    dvj[d] += p * sd[i * (D + 1) + d];
+            for (int r = 0; r < D / 32; ++r) aq[r] = ak[r] = av[r] = 0.f;
+            for (int j = 0; j < L; ++j) {
+                const float ds_ij = ss[i * L + j], ds_ji = ss[j * L + i], p_ji = sp[j * L + i];
+#pragma unroll
+                for (int r = 0; r < D / 32; ++r) {
+                    const int d = lane + 32 * r;
+                    aq[r] += ds_ij * sk[j * (D + 1) + d];   // dQ_i = sum_j dS_ij K_j
+                    ak[r] += ds_ji * sq[j * (D + 1) + d];   // dK_i = sum_j dS_ji Q_j
+                    av[r] += p_ji * sd[j * (D + 1) + d];    // dV_i = sum_j P_ji dO_j
                 }
             }
-            // dQ_i = sum_j dS_ij k_j : lane owns dims lane, lane+32
-            float acc[D / 32];
+            const int64_t off = base + i * a.seq_stride;
 #pragma unroll
-            for (int r = 0; r < D / 32; ++r) acc[r] = 0.f;
-            for (int j = 0; j < L; ++j) {
-                const float dsj = __shfl_sync(0xffffffffu, ds, j);
-#pragma unroll
-                for (int r = 0; r < D / 32; ++r) acc[r] += dsj * sk[j * (D + 1) + lane + 32 * r];
-            }
-            __nv_bfloat16* qrow = dq + base + i * a.seq_stride;
-#pragma unroll
-            for (int r = 0; r < D / 32; ++r) qrow[lane + 32 * r] = __float2bfloat16_rn(acc[r]);
-        }
-        if (lane < L) {
-            __nv_bfloat162* krow = reinterpret_cast<__nv_bfloat162*>(dk + base + lane * a.seq_stride);
-            __nv_bfloat162* vrow = reinterpret_cast<__nv_bfloat162*>(dv + base + lane * a.seq_stride);
-#pragma unroll
-            for (int d = 0; d < D / 2; ++d) {
-                krow[d] = __floats2bfloat162_rn(dkj[2 * d], dkj[2 * d + 1]);
-                vrow[d] = __floats2bfloat162_rn(dvj[2 * d], dvj[2 * d + 1]);
+            for (int r = 0; r < D / 32; ++r) {
+                dq[off + lane + 32 * r] = __float2bfloat16_rn(aq[r]);
+                dk[off + lane + 32 * r] = __float2bfloat16_rn(ak[r]);
+                dv[off + lane + 32 * r] = __float2bfloat16_rn(av[r]);
             }
         }
     }
@@ -178,35 +180,40 @@ __global__ void attn_small_bwd_kernel(const __nv_bfloat16* __restrict__ q, const
 
 using namespace t2v;
 
+static int attn_small_config(int L, int D, int tiles, int extra_floats, int& warps, size_t& smem) {
+    // as many warps per block as fit ~100 KB, so that two blocks share an SM
+    const size_t per_warp = (size_t(tiles) * L * (D + 1) + extra_floats) * sizeof(float);
+    warps = int(std::min<size_t>(8, std::max<size_t>(1, (100 * 1024) / per_warp)));
+    smem = per_warp * warps;
+    return 0;
+}
+
 extern "C" {
 
 int t2v_attn_small_fwd(const void* q, const void* k, const void* v, void* o, int64_t nseq, int32_t inner, int64_t outer_stride,
                        int64_t inner_stride, int64_t seq_stride, int32_t heads, int32_t L, int32_t D, void* stream) {
     if (L < 1 || L > kMaxL) return fail(-2, "attn_small: L=%d out of range (1..%d)", L, kMaxL);
     if (D != 64 && D != 32) return fail(-2, "attn_small: head_dim %d unsupported (32 or 64)", D);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(attn_small_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        cudaFuncSetAttribute(attn_small_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        attr_done = true;
+    }
     SeqAddr a{outer_stride, inner_stride, seq_stride, inner};
+    int warps;
+    size_t smem;
+    attn_small_config(L, D, 3, 0, warps, smem);
     const int64_t total = nseq * heads;
-    const int grid = int(std::min<int64_t>((total + kWarpsPerBlock - 1) / kWarpsPerBlock, 148 * 8));
-    const size_t smem = size_t(kWarpsPerBlock) * 3 * kMaxL * (D + 1) * sizeof(float);
+    const int grid = int(std::min<int64_t>((total + warps - 1) / warps, 148 * 8));
     const float scale = 1.0f / sqrtf(float(D));
     auto Q = static_cast<const __nv_bfloat16*>(q);
     auto K = static_cast<const __nv_bfloat16*>(k);
     auto V = static_cast<const __nv_bfloat16*>(v);
     auto O = static_cast<__nv_bfloat16*>(o);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(attn_small_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             int(size_t(kWarpsPerBlock) * 3 * kMaxL * 65 * sizeof(float)));
-        cudaFuncSetAttribute(attn_small_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             int(size_t(kWarpsPerBlock) * 3 * kMaxL * 33 * sizeof(float)));
-        attr_done = true;
-    }
-    if (D == 64) {
-        attn_small_fwd_kernel<64><<<grid, kWarpsPerBlock * 32, smem, st>>>(Q, K, V, O, a, nseq, heads, L, scale);
-    } else {
-        attn_small_fwd_kernel<32><<<grid, kWarpsPerBlock * 32, smem, st>>>(Q, K, V, O, a, nseq, heads, L, scale);
-    }
+    if (D == 64) attn_small_fwd_kernel<64><<<grid, warps * 32, smem, st>>>(Q, K, V, O, a, nseq, heads, L, scale);
+    else attn_small_fwd_kernel<32><<<grid, warps * 32, smem, st>>>(Q, K, V, O, a, nseq, heads, L, scale);
     return launch_checked(int(cudaGetLastError()), "attn_small_fwd");
 }
 
@@ -215,27 +222,24 @@ int t2v_attn_small_bwd(const void* q, const void* k, const void* v, const void* 
                        int32_t D, void* stream) {
     if (L < 1 || L > kMaxL) return fail(-2, "attn_small: L=%d out of range (1..%d)", L, kMaxL);
     if (D != 64 && D != 32) return fail(-2, "attn_small: head_dim %d unsupported (32 or 64)", D);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(attn_small_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        cudaFuncSetAttribute(attn_small_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        attr_done = true;
+    }
     SeqAddr a{outer_stride, inner_stride, seq_stride, inner};
+    int warps;
+    size_t smem;
+    attn_small_config(L, D, 4, 2 * L * L, warps, smem);
     const int64_t total = nseq * heads;
-    const int grid = int(std::min<int64_t>((total + kWarpsPerBlock - 1) / kWarpsPerBlock, 148 * 8));
-    const size_t smem = size_t(kWarpsPerBlock) * 4 * kMaxL * (D + 1) * sizeof(float);
+    const int grid = int(std::min<int64_t>((total + warps - 1) / warps, 148 * 8));
     const float scale = 1.0f / sqrtf(float(D));
     auto B = [](const void* p) { return static_cast<const __nv_bfloat16*>(p); };
     auto W = [](void* p) { return static_cast<__nv_bfloat16*>(p); };
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(attn_small_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             int(size_t(kWarpsPerBlock) * 4 * kMaxL * 65 * sizeof(float)));
-        cudaFuncSetAttribute(attn_small_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             int(size_t(kWarpsPerBlock) * 4 * kMaxL * 33 * sizeof(float)));
-        attr_done = true;
-    }
-    if (D == 64) {
-        attn_small_bwd_kernel<64><<<grid, kWarpsPerBlock * 32, smem, st>>>(B(q), B(k), B(v), B(dout), W(dq), W(dk), W(dv), a, nseq, heads, L, scale);
-    } else {
-        attn_small_bwd_kernel<32><<<grid, kWarpsPerBlock * 32, smem, st>>>(B(q), B(k), B(v), B(dout), W(dq), W(dk), W(dv), a, nseq, heads, L, scale);
-    }
+    if (D == 64) attn_small_bwd_kernel<64><<<grid, warps * 32, smem, st>>>(B(q), B(k), B(v), B(dout), W(dq), W(dk), W(dv), a, nseq, heads, L, scale);
+    else attn_small_bwd_kernel<32><<<grid, warps * 32, smem, st>>>(B(q), B(k), B(v), B(dout), W(dq), W(dk), W(dv), a, nseq, heads, L, scale);
     return launch_checked(int(cudaGetLastError()), "attn_small_bwd");
 }
 

@@ -25,28 +25,31 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 __device__ __forceinline__ float sigmoidf_(float z) { return 1.0f / (1.0f + __expf(-z)); }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm
-// Per-channel partial sums over a chunk of pixels.  MODE 0: (sum x, sum x^2).  MODE 1 (backward): (sum dz, sum dz*xhat)
-// where dz = dy * silu'(a x + b) (or dy) and xhat = (x - mean) rstd.
-// Thread layout: V = C/8 channel vectors; thread owns vector tid % V and pixel lane tid / V.
+// Two kernels per direction (plus one memset of the [S][C][2] accumulator):
+//   gn_partial_kernel : per-channel sums over a chunk of pixels, reduced in shared memory, then ONE atomicAdd per
+//                       channel per block into accum[S][C][2].   MODE 0: (sum x, sum x^2); MODE 1: (sum dz, sum dz*xhat)
+//   gn_*_apply_kernel : every block first finalises its sample's statistics / coefficients from accum in shared memory
+//                       (2C..5C floats, fp64 for the group combine), then streams its own chunk of pixels.
+// Thread layout of the streaming loops: V = C/8 channel vectors; thread owns vector tid % V and pixel lane tid / V.
 template <int MODE>
 __global__ void gn_partial_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                   const float* __restrict__ ab,   // [S][C][2] (a,b) for z = a x + b   (MODE 1)
                                   const float* __restrict__ stat, // [S][G][2] (mean, rstd)            (MODE 1)
-                                  float* __restrict__ partial,    // [S][chunks][C][2]
+                                  float* __restrict__ accum,      // [S][C][2]
                                   int64_t P, int C, int G, int chunk_pixels, int silu) {
     extern __shared__ float sh[];  // [2][C]
-    const int s = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+    const int s = blockIdx.y, chunk = blockIdx.x;
     const int V = C >> 3;
     const int lanes = blockDim.x / V;
     const int cv = threadIdx.x % V, pl = threadIdx.x / V;
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
     __syncthreads();
-    float acc0[8], acc1[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc0[j] = acc1[j] = 0.f;
     const int64_t p0 = int64_t(chunk) * chunk_pixels;
     const int64_t p1 = min(P, p0 + chunk_pixels);
     if (pl < lanes) {
+        float acc0[8], acc1[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc0[j] = acc1[j] = 0.f;
         float a[8], b[8], mean[8], rstd[8];
         if (MODE == 1) {
             const int cpg = C / G;
@@ -93,160 +96,145 @@ __global__ void gn_partial_kernel(const __nv_bfloat16* __restrict__ x, const __n
         }
     }
     __syncthreads();
-    float* out = partial + (int64_t(s) * chunks + chunk) * C * 2;
+    float* out = accum + int64_t(s) * C * 2;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        out[2 * c] = sh[c];
-        out[2 * c + 1] = sh[C + c];
+        atomicAdd(out + 2 * c, sh[c]);
+        atomicAdd(out + 2 * c + 1, sh[C + c]);
     }
 }
 
-// Forward finalize: one block per sample.  Reduces chunk partials -> (mean, rstd) per group and the per-channel
-// affine (a, b) with y = act(a x + b).
-__global__ void gn_fwd_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma,
-                                       const float* __restrict__ beta, float* __restrict__ stat, float* __restrict__ ab,
-                                       int64_t P, int C, int G, int chunks, float eps) {
-    extern __shared__ float sh[];  // [2][C] then [2][G]
-    const int s = blockIdx.x;
-    float* gs = sh + 2 * C;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        double a0 = 0, a1 = 0;
-        for (int k = 0; k < chunks; ++k) {
-            const float* pp = partial + ((int64_t(s) * chunks + k) * C + c) * 2;
-            a0 += pp[0];
-            a1 += pp[1];
-        }
-        sh[c] = float(a0);
-        sh[C + c] = float(a1);
-    }
-    __syncthreads();
+// Forward apply: finalise (mean, rstd) per group and the per-channel affine (a, b) in shared memory, then y = act(a x + b).
+__global__ void gn_fwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ accum,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                    float* __restrict__ stat, float* __restrict__ ab, int64_t P, int C, int G, int chunk_pixels,
+                                    float eps, int silu) {
+    extern __shared__ float sh[];  // a[C], b[C], gmean[G], grstd[G]
+    float* sa = sh;
+    float* sb = sh + C;
+    float* gm = sh + 2 * C;
+    float* gr = gm + G;
+    const int s = blockIdx.y;
     const int cpg = C / G;
+    const float* acc = accum + int64_t(s) * C * 2;
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
         double a0 = 0, a1 = 0;
         for (int j = 0; j < cpg; ++j) {
-            a0 += sh[g * cpg + j];
-            a1 += sh[C + g * cpg + j];
+            a0 += acc[2 * (g * cpg + j)];
+            a1 += acc[2 * (g * cpg + j) + 1];
         }
         const double n = double(P) * cpg;
         const double mean = a0 / n;
         double var = a1 / n - mean * mean;
         if (var < 0) var = 0;
         const float rstd = float(1.0 / sqrt(var + double(eps)));
-        gs[g] = float(mean);
-        gs[G + g] = rstd;
-        stat[(int64_t(s) * G + g) * 2] = float(mean);
-        stat[(int64_t(s) * G + g) * 2 + 1] = rstd;
+        gm[g] = float(mean);
+        gr[g] = rstd;
+        if (blockIdx.x == 0) {
+            stat[(int64_t(s) * G + g) * 2] = float(mean);
+            stat[(int64_t(s) * G + g) * 2 + 1] = rstd;
+        }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int g = c / cpg;
-        const float a = gs[G + g] * gamma[c];
-        ab[(int64_t(s) * C + c) * 2] = a;
-        ab[(int64_t(s) * C + c) * 2 + 1] = beta[c] - gs[g] * a;
-    }
-}
-
-// y = act(a x + b), elementwise over [S][P][C].
-__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ ab,
-                                __nv_bfloat16* __restrict__ y, int64_t P, int C, int64_t total_vec, int silu) {
-    const int V = C >> 3;
-    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total_vec; i += int64_t(gridDim.x) * blockDim.x) {
-        const int cv = int(i % V);
-        const int64_t s = (i / V) / P;
-        float v[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), v);
-        const float4* abp = reinterpret_cast<const float4*>(ab + (s * C + cv * 8) * 2);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 q = __ldg(abp + j);
-            float z0 = q.x * v[2 * j] + q.y, z1 = q.z * v[2 * j + 1] + q.w;
-            if (silu) {
-                z0 *= sigmoidf_(z0);
-                z1 *= sigmoidf_(z1);
-            }
-            v[2 * j] = z0;
-            v[2 * j + 1] = z1;
+        const float a = gr[g] * gamma[c];
+        const float b = beta[c] - gm[g] * a;
+        sa[c] = a;
+        sb[c] = b;
+        if (blockIdx.x == 0) {
+            ab[(int64_t(s) * C + c) * 2] = a;
+            ab[(int64_t(s) * C + c) * 2 + 1] = b;
         }
-        reinterpret_cast<uint4*>(y)[i] = pack8(v);
-    }
-}
-
-// Backward finalize: one block per sample.  Produces the per-channel coefficients (pc, qc, rc) with
-//   dx = pc * dz + qc * x + rc, and accumulates dgamma / dbeta.
-__global__ void gn_bwd_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma,
-                                       const float* __restrict__ stat, float* __restrict__ coef /*[S][C][4]*/,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t P, int C, int G,
-                                       int chunks) {
-    extern __shared__ float sh[];  // [2][C] then [2][G]
-    const int s = blockIdx.x;
-    float* gs = sh + 2 * C;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        double a0 = 0, a1 = 0;
-        for (int k = 0; k < chunks; ++k) {
-            const float* pp = partial + ((int64_t(s) * chunks + k) * C + c) * 2;
-            a0 += pp[0];
-            a1 += pp[1];
-        }
-        sh[c] = float(a0);      // sum dz
-        sh[C + c] = float(a1);  // sum dz * xhat
-        if (dbeta) atomicAdd(dbeta + c, float(a0));
-        if (dgamma) atomicAdd(dgamma + c, float(a1));
     }
     __syncthreads();
+    const int V = C >> 3;
+    const int64_t p0 = int64_t(blockIdx.x) * chunk_pixels, p1 = min(P, p0 + chunk_pixels);
+    const int64_t nvec = (p1 - p0) * V;
+    const uint4* xs = reinterpret_cast<const uint4*>(x + (int64_t(s) * P + p0) * C);
+    uint4* ys = reinterpret_cast<uint4*>(y + (int64_t(s) * P + p0) * C);
+    for (int64_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+        const int cv = int(i % V);
+        float v[8];
+        unpack8(__ldg(xs + i), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float z = sa[cv * 8 + j] * v[j] + sb[cv * 8 + j];
+            if (silu) z *= sigmoidf_(z);
+            v[j] = z;
+        }
+        ys[i] = pack8(v);
+    }
+}
+
+// Backward apply: dx = pc * dz + qc * x + rc (+ add), dz = dy * silu'(a x + b); block 0 of each sample also
+// accumulates dgamma / dbeta.
+__global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                    const float* __restrict__ accum, const float* __restrict__ gamma, const float* __restrict__ stat,
+                                    const float* __restrict__ ab, const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ dx,
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t P, int C, int G, int chunk_pixels,
+                                    int silu) {
+    extern __shared__ float sh[];  // pc[C], qc[C], rc[C], a[C], b[C], s1[G], s2[G]
+    float* pc = sh;
+    float* qc = sh + C;
+    float* rc = sh + 2 * C;
+    float* sa = sh + 3 * C;
+    float* sb = sh + 4 * C;
+    float* g1 = sh + 5 * C;
+    float* g2 = g1 + G;
+    const int s = blockIdx.y;
     const int cpg = C / G;
+    const float* acc = accum + int64_t(s) * C * 2;  // (sum dz, sum dz*xhat) per channel
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
         double s1 = 0, s2 = 0;
         for (int j = 0; j < cpg; ++j) {
             const int c = g * cpg + j;
-            s1 += double(gamma[c]) * sh[c];
-            s2 += double(gamma[c]) * sh[C + c];
+            s1 += double(gamma[c]) * acc[2 * c];
+            s2 += double(gamma[c]) * acc[2 * c + 1];
         }
-        gs[g] = float(s1);
-        gs[G + g] = float(s2);
+        g1[g] = float(s1);
+        g2[g] = float(s2);
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int g = c / cpg;
         const float mean = stat[(int64_t(s) * G + g) * 2], rstd = stat[(int64_t(s) * G + g) * 2 + 1];
         const float invn = 1.0f / (float(P) * cpg);
-        const float q = -rstd * rstd * gs[G + g] * invn;
-        float* o = coef + (int64_t(s) * C + c) * 4;
-        o[0] = rstd * gamma[c];
-        o[1] = q;
-        o[2] = -rstd * gs[g] * invn - q * mean;
-        o[3] = 0.f;
+        const float q = -rstd * rstd * g2[g] * invn;
+        pc[c] = rstd * gamma[c];
+        qc[c] = q;
+        rc[c] = -rstd * g1[g] * invn - q * mean;
+        sa[c] = ab[(int64_t(s) * C + c) * 2];
+        sb[c] = ab[(int64_t(s) * C + c) * 2 + 1];
+        if (blockIdx.x == 0) {
+            if (dbeta) atomicAdd(dbeta + c, acc[2 * c]);
+            if (dgamma) atomicAdd(dgamma + c, acc[2 * c + 1]);
+        }
     }
-}
-
-// dx = pc * dz + qc * x + rc (+ add), dz = dy * silu'(a x + b).
-__global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
-                                    const float* __restrict__ ab, const float* __restrict__ coef,
-                                    const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ dx, int64_t P, int C,
-                                    int64_t total_vec, int silu) {
+    __syncthreads();
     const int V = C >> 3;
-    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total_vec; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t p0 = int64_t(blockIdx.x) * chunk_pixels, p1 = min(P, p0 + chunk_pixels);
+    const int64_t nvec = (p1 - p0) * V;
+    const int64_t base = (int64_t(s) * P + p0) * V;
+    for (int64_t i = threadIdx.x; i < nvec; i += blockDim.x) {
         const int cv = int(i % V);
-        const int64_t s = (i / V) / P;
         float v[8], d[8], r[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), v);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dy) + i), d);
-        if (add) unpack8(__ldg(reinterpret_cast<const uint4*>(add) + i), r);
-        const float2* abp = reinterpret_cast<const float2*>(ab + (s * C + cv * 8) * 2);
-        const float4* cp = reinterpret_cast<const float4*>(coef + (s * C + cv * 8) * 4);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x) + base + i), v);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dy) + base + i), d);
+        if (add) unpack8(__ldg(reinterpret_cast<const uint4*>(add) + base + i), r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
+            const int c = cv * 8 + j;
             float dz = d[j];
             if (silu) {
-                const float2 q = __ldg(abp + j);
-                const float z = q.x * v[j] + q.y;
+                const float z = sa[c] * v[j] + sb[c];
                 const float sg = sigmoidf_(z);
                 dz *= sg * (1.f + z * (1.f - sg));
             }
-            const float4 c4 = __ldg(cp + j);
-            float o = c4.x * dz + c4.y * v[j] + c4.z;
+            float o = pc[c] * dz + qc[c] * v[j] + rc[c];
             if (add) o += r[j];
             v[j] = o;
         }
-        reinterpret_cast<uint4*>(dx)[i] = pack8(v);
+        reinterpret_cast<uint4*>(dx)[base + i] = pack8(v);
     }
 }
 
@@ -399,11 +387,21 @@ static int gn_block(int C) {
 }
 
 static void gn_chunks(int S, int64_t P, int& chunk_pixels, int& chunks) {
-    // aim for >= ~4 blocks per SM overall, at least 16 pixels per chunk
+    // aim for ~4 blocks per SM overall, at least 32 pixels per chunk
     const int64_t want = std::max<int64_t>(1, (4 * 148 + S - 1) / S);
-    int64_t cp = std::max<int64_t>(16, (P + want - 1) / want);
+    int64_t cp = std::max<int64_t>(32, (P + want - 1) / want);
     chunk_pixels = int(std::min<int64_t>(cp, P));
     chunks = int((P + chunk_pixels - 1) / chunk_pixels);
+}
+
+static void gn_set_attrs() {
+    static bool done = false;
+    if (done) return;
+    cudaFuncSetAttribute(gn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(gn_fwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(gn_partial_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(gn_partial_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    done = true;
 }
 
 }  // namespace t2v
@@ -413,26 +411,25 @@ using namespace t2v;
 extern "C" {
 
 int64_t t2v_groupnorm_workspace_bytes(int32_t S, int64_t P, int32_t C) {
-    int cp, ch;
-    gn_chunks(S, P, cp, ch);
-    return int64_t(S) * ch * C * 2 * sizeof(float) + int64_t(S) * C * 4 * sizeof(float) + 256;
+    (void)P;
+    return int64_t(S) * C * 2 * sizeof(float) + 256;
 }
 
 int t2v_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stat, float* ab, void* workspace,
                       int32_t S, int64_t P, int32_t C, int32_t G, float eps, int32_t silu, void* stream_) {
     if (C % 8 || C % G || C / 8 > 1024) return fail(-2, "groupnorm: C=%d G=%d unsupported", C, G);
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    gn_set_attrs();
     int cp, chunks;
     gn_chunks(S, P, cp, chunks);
-    float* partial = static_cast<float*>(workspace);
+    float* accum = static_cast<float*>(workspace);
+    cudaMemsetAsync(accum, 0, size_t(S) * C * 2 * sizeof(float), st);
     const int bs = gn_block(C);
     gn_partial_kernel<0><<<dim3(chunks, S), bs, 2 * C * sizeof(float), st>>>(
-        static_cast<const __nv_bfloat16*>(x), nullptr, nullptr, nullptr, partial, P, C, G, cp, 0);
-    gn_fwd_finalize_kernel<<<S, 256, (2 * C + 2 * G) * sizeof(float), st>>>(partial, gamma, beta, stat, ab, P, C, G, chunks, eps);
-    const int64_t tv = int64_t(S) * P * (C / 8);
-    const int grid = int(std::min<int64_t>((tv + 255) / 256, 148 * 16));
-    gn_apply_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ab, static_cast<__nv_bfloat16*>(y), P, C, tv, silu);
-    count_launch(2);
+        static_cast<const __nv_bfloat16*>(x), nullptr, nullptr, nullptr, accum, P, C, G, cp, 0);
+    gn_fwd_apply_kernel<<<dim3(chunks, S), 256, (2 * C + 2 * G) * sizeof(float), st>>>(
+        static_cast<const __nv_bfloat16*>(x), accum, gamma, beta, static_cast<__nv_bfloat16*>(y), stat, ab, P, C, G, cp, eps, silu);
+    count_launch(1);
     return launch_checked(int(cudaGetLastError()), "groupnorm_fwd");
 }
 
@@ -441,19 +438,18 @@ int t2v_groupnorm_bwd(const void* dy, const void* x, const float* gamma, const f
                       int32_t silu, void* stream_) {
     if (C % 8 || C % G || C / 8 > 1024) return fail(-2, "groupnorm: C=%d G=%d unsupported", C, G);
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    gn_set_attrs();
     int cp, chunks;
     gn_chunks(S, P, cp, chunks);
-    float* partial = static_cast<float*>(workspace);
-    float* coef = partial + int64_t(S) * chunks * C * 2;
+    float* accum = static_cast<float*>(workspace);
+    cudaMemsetAsync(accum, 0, size_t(S) * C * 2 * sizeof(float), st);
     const int bs = gn_block(C);
     gn_partial_kernel<1><<<dim3(chunks, S), bs, 2 * C * sizeof(float), st>>>(
-        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), ab, stat, partial, P, C, G, cp, silu);
-    gn_bwd_finalize_kernel<<<S, 256, (2 * C + 2 * G) * sizeof(float), st>>>(partial, gamma, stat, coef, dgamma, dbeta, P, C, G, chunks);
-    const int64_t tv = int64_t(S) * P * (C / 8);
-    const int grid = int(std::min<int64_t>((tv + 255) / 256, 148 * 16));
-    gn_bwd_apply_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), ab, coef,
-                                              static_cast<const __nv_bfloat16*>(add), static_cast<__nv_bfloat16*>(dx), P, C, tv, silu);
-    count_launch(2);
+        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), ab, stat, accum, P, C, G, cp, silu);
+    gn_bwd_apply_kernel<<<dim3(chunks, S), 256, (5 * C + 2 * G) * sizeof(float), st>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), accum, gamma, stat, ab,
+        static_cast<const __nv_bfloat16*>(add), static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, P, C, G, cp, silu);
+    count_launch(1);
     return launch_checked(int(cudaGetLastError()), "groupnorm_bwd");
 }
 
