@@ -54,10 +54,27 @@ int choose_block_n(int64_t row_tiles, int ncols, bool mn_major_b) {
     return best;
 }
 
+// Split-K factor for accumulate-mode problems: minimise  waves(base_tiles * s) * (k-blocks per split * T_kblock + T_epilogue).
+int choose_splits(int64_t base_tiles, int kb_total) {
+    const int sms = device_sm_count();
+    int best = 1;
+    double best_cost = 1e30;
+    for (int s = 1; s <= kb_total && s <= 128; ++s) {
+        const int64_t waves = (base_tiles * s + sms - 1) / sms;
+        const int kper = (kb_total + s - 1) / s;
+        const double cost = double(waves) * (kper * 320.0 + 2500.0);
+        if (cost < best_cost - 1e-9) {
+            best_cost = cost;
+            best = s;
+        }
+    }
+    return best;
+}
+
 void finish_common(GemmParams& p, bool b_mn) {
     p.stage_bytes_a = kBlockM * 128;
     p.stage_bytes_b = b_mn ? ((p.block_n + 63) / 64) * 8192 : p.block_n * 128;
-    const int budget = 232448 - 1024 - 256;
+    const int budget = 232448 - 1024 - 256 - kEpilogueStagingBytes;
     p.num_stages = std::min<int>(kMaxStages, budget / (p.stage_bytes_a + p.stage_bytes_b));
     int64_t tiles = 1;
     for (int i = 0; i < 6; ++i) tiles *= p.tdim[i];
@@ -245,7 +262,7 @@ int t2v_conv_wgrad(const void* x, const void* dy, float* dw, int32_t N, int32_t 
     p.tdim[2] = KW;
     p.tdim[3] = KH;
     const int64_t base_tiles = int64_t(p.tdim[0]) * p.tdim[1] * KW * KH;
-    int splits = static_cast<int>(std::min<int64_t>(kb_total, std::max<int64_t>(1, (2 * device_sm_count() + base_tiles - 1) / base_tiles)));
+    int splits = choose_splits(base_tiles, kb_total);
     p.kb_per_split = (kb_total + splits - 1) / splits;
     splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
     p.tdim[4] = splits;
@@ -306,7 +323,7 @@ int t2v_bgemm(const T2VMat* A, const T2VMat* B, void* C, int64_t ldc, int64_t c_
     int splits = 1;
     if (out_mode == OUT_F32_RED) {
         const int64_t base_tiles = int64_t(p.tdim[0]) * p.tdim[1] * Z1 * Z2;
-        splits = static_cast<int>(std::min<int64_t>(p.kdim[0], std::max<int64_t>(1, (2 * device_sm_count() + base_tiles - 1) / base_tiles)));
+        splits = choose_splits(base_tiles, p.kdim[0]);
         p.kb_per_split = (p.kdim[0] + splits - 1) / splits;
         splits = (p.kdim[0] + p.kb_per_split - 1) / p.kb_per_split;
         p.tdim[2] = splits;

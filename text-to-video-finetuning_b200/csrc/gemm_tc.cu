@@ -2,7 +2,8 @@
 //
 //   warp 0 : TMA producer   (one elected lane) - fills the smem ring, one mbarrier pair per stage
 //   warp 1 : MMA issuer     (one elected lane) - tcgen05.mma into one of two TMEM accumulator stages
-//   warps 2-5 : epilogue    (128 threads, thread <-> accumulator row) - tcgen05.ld, fused epilogue, global stores
+//   warps 2-9 : epilogue    (2 x 128 threads, thread <-> accumulator row, the two groups split the columns) -
+//               tcgen05.ld, fused epilogue, smem-staged coalesced global stores / red.add
 //
 // The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
 #include "gemm_tc.cuh"
@@ -51,9 +52,9 @@ __device__ __forceinline__ void issue_operand(const TmaOperand& op, const int32_
     int32_t c[5];
 #pragma unroll
     for (int d = 0; d < 5; ++d) c[d] = tile_c[d] + kv[0] * op.kcoef[d][0] + kv[1] * op.kcoef[d][1] + kv[2] * op.kcoef[d][2];
-    for (int b = 0; b < op.nbox; ++b) {
+    for (int b = 0; b < op.nbox; ++b) {  // boxes of an MN-major operand always advance along dimension 0
         tma_load(op.rank, smem_dst + b * op.box_bytes, &op.map, bar, c);
-        c[op.box_dim] += op.box_step;
+        c[0] += op.box_step;
     }
 }
 
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], 128);
+            mbar_init(&acc_empty[s], 256);
         }
         fence_mbar_init();
     }
@@ -107,17 +108,23 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                 tile_coords(p.b, tv, cb);
                 int32_t kb0, kb1;
                 k_range(p, tv, kb0, kb1);
+                // k-loop variables advance as a mixed-radix counter (no div/mod per k-block)
+                int32_t kv[3];
+                kv[0] = kb0 % p.kdim[0];
+                kv[1] = (kb0 / p.kdim[0]) % p.kdim[1];
+                kv[2] = kb0 / (p.kdim[0] * p.kdim[1]);
                 for (int32_t kb = kb0; kb < kb1; ++kb) {
-                    int32_t kv[3];
-                    int32_t r = kb;
-                    kv[0] = r % p.kdim[0];
-                    r /= p.kdim[0];
-                    kv[1] = r % p.kdim[1];
-                    kv[2] = r / p.kdim[1];
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], tx_bytes);
                     issue_operand(p.a, ca, kv, smem_a + static_cast<size_t>(stage) * p.stage_bytes_a, &full_bar[stage]);
                     issue_operand(p.b, cb, kv, smem_b + static_cast<size_t>(stage) * p.stage_bytes_b, &full_bar[stage]);
+                    if (++kv[0] == p.kdim[0]) {
+                        kv[0] = 0;
+                        if (++kv[1] == p.kdim[1]) {
+                            kv[1] = 0;
+                            ++kv[2];
+                        }
+                    }
                     if (++stage == static_cast<uint32_t>(S)) {
                         stage = 0;
                         phase ^= 1;
@@ -165,14 +172,27 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
-        const uint32_t quad = warp & 3u;  // TMEM lane quadrant this warp may access
+        // ------------------------------------------------------------------ epilogue (warps 2..9)
+        // Two groups of four warps split the accumulator columns; within a group warp w owns TMEM lanes 32*(w%4)..+31,
+        // i.e. thread <-> output row.  Rows are strided in global memory, so every 32-column chunk goes through a
+        // per-warp swizzled staging tile: residual in / result out are moved with full 128-byte lines.
+        const uint32_t ew = warp - 2u;
+        const uint32_t quad = warp & 3u;
+        const uint32_t grp = ew >> 2;
         const uint32_t row = quad * 32u + lane;
         const int32_t rw = static_cast<int32_t>(row) % p.bw;
         const int32_t rh = (static_cast<int32_t>(row) / p.bw) % p.bh;
         const int32_t rn = static_cast<int32_t>(row) / (p.bw * p.bh);
         const bool has_bias = p.flags & EPI_BIAS, has_rb = p.flags & EPI_ROWBIAS, has_res = p.flags & EPI_RESIDUAL;
         const bool vec = p.flags & EPI_VEC;
+        const int nchunks = (p.block_n + 31) >> 5;
+        const int c_begin = grp == 0 ? 0 : (nchunks + 1) >> 1;
+        const int c_end = grp == 0 ? (nchunks + 1) >> 1 : nchunks;
+        uint8_t* stg = reinterpret_cast<uint8_t*>(tmem_slot + 4) + ew * 4096u;  // 32 rows x <=128 B
+        const int esz = p.out_mode == OUT_BF16 ? 2 : 4;
+        const int cpr = esz * 2;  // 16-byte chunks per 32-column row: 4 (bf16) or 8 (fp32)
+        // swizzled position of logical chunk j of row r in a dense [32][cpr] chunk array
+        auto phys = [](int r, int j, int n) { return (r * n + (j ^ (((r * n) >> 3) & (n - 1)))) * 16; };
         uint32_t it = 0;
         for (int32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             TileVars tv;
@@ -188,70 +208,113 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
             mbar_wait(&acc_full[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + as * 256u;
-            for (int32_t c0 = 0; c0 < p.block_n; c0 += 16) {
-                uint32_t r[16];
-                __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent stores below
-                tmem_ld16(taddr + c0, r);
+            for (int ch = c_begin; ch < c_end; ++ch) {
+                const int32_t col = col0 + ch * 32;
+                const int32_t cvalid = min(32, min(p.block_n - ch * 32, p.ncols - col));  // valid columns of this chunk
+                __syncwarp();
+                if (vec && has_res && cvalid > 0) {  // residual: coalesced global -> staging (bf16, 4 chunks per row)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = (lane >> 2) + 8 * i, j = lane & 3;
+                        const int64_t off_r = __shfl_sync(0xffffffffu, off, r);
+                        const bool ok_r = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, r);
+                        uint4 q = make_uint4(0, 0, 0, 0);
+                        if (ok_r && j * 8 + 8 <= cvalid)
+                            q = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + off_r + col + j * 8));
+                        *reinterpret_cast<uint4*>(stg + phys(r, j, 4)) = q;
+                    }
+                }
+                uint32_t acc[32];
+                tmem_ld32(taddr + ch * 32, acc);
                 tmem_ld_wait();
-                const int32_t col = col0 + c0;
-                if (!row_ok || col >= p.ncols) continue;
-                float v[16];
+                if (cvalid <= 0) continue;
+                float v[32];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-                const bool full = vec && (col + 16 <= p.ncols);
-                if (full) {
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * p.alpha;
+                if (vec) {
                     if (has_bias) {
-                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 b = __ldg(b4 + j);
-                            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                        for (int j = 0; j < 8; ++j) {
+                            if (j * 4 + 4 <= cvalid) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j);
+                                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                            }
                         }
                     }
-                    if (has_rb) {
+                    if (has_rb && row_ok) {
                         const float4* b4 = reinterpret_cast<const float4*>(p.rowbias + (gn / p.rb_div) * p.rb_ld + col);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 b = __ldg(b4 + j);
-                            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                        for (int j = 0; j < 8; ++j) {
+                            if (j * 4 + 4 <= cvalid) {
+                                const float4 b = __ldg(b4 + j);
+                                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                            }
                         }
                     }
                     if (has_res) {
-                        const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + off + col);
+                        __syncwarp();
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const uint4 q = __ldg(r4 + j);
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 q = *reinterpret_cast<const uint4*>(stg + phys(lane, j, 4));
                             v[8 * j + 0] += bf16_lo(q.x); v[8 * j + 1] += bf16_hi(q.x);
                             v[8 * j + 2] += bf16_lo(q.y); v[8 * j + 3] += bf16_hi(q.y);
                             v[8 * j + 4] += bf16_lo(q.z); v[8 * j + 5] += bf16_hi(q.z);
                             v[8 * j + 6] += bf16_lo(q.w); v[8 * j + 7] += bf16_hi(q.w);
                         }
+                        __syncwarp();
                     }
-                    if (p.out_mode == OUT_BF16) {
-                        uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + off + col);
+                    // own row -> staging
+                    if (esz == 2) {
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
+                        for (int j = 0; j < 4; ++j) {
                             uint4 q;
                             q.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
                             q.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
                             q.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
                             q.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-                            o4[j] = q;
+                            *reinterpret_cast<uint4*>(stg + phys(lane, j, 4)) = q;
                         }
-                    } else if (p.out_mode == OUT_F32) {
-                        float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(p.out) + off + col);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     } else {
-                        float* o = static_cast<float*>(p.out) + off + col;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) red_add_f32x4(o + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4*>(stg + phys(lane, j, 8)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     }
-                } else {
-                    // scalar tail / unaligned path
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (col + j >= p.ncols) break;
+                    __syncwarp();
+                    // staging -> global, 16 bytes per lane, full lines per row
+                    const int epc = 16 / esz;  // elements per 16-byte chunk
+                    for (int i = 0; i < cpr; ++i) {
+                        const int r = lane / cpr + (32 / cpr) * i, j = lane % cpr;
+                        const int64_t off_r = __shfl_sync(0xffffffffu, off, r);
+                        const bool ok_r = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, r);
+                        const int nval = cvalid - j * epc;  // valid elements in this chunk
+                        if (!ok_r || nval <= 0) continue;
+                        const uint4 q = *reinterpret_cast<const uint4*>(stg + phys(r, j, cpr));
+                        if (nval >= epc) {
+                            if (p.out_mode == OUT_BF16) {
+                                *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + off_r + col + j * 8) = q;
+                            } else if (p.out_mode == OUT_F32) {
+                                *reinterpret_cast<uint4*>(static_cast<float*>(p.out) + off_r + col + j * 4) = q;
+                            } else {
+                                red_add_f32x4(static_cast<float*>(p.out) + off_r + col + j * 4, __uint_as_float(q.x), __uint_as_float(q.y),
+                                              __uint_as_float(q.z), __uint_as_float(q.w));
+                            }
+                        } else {  // ragged last chunk: element-wise
+                            const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+                            for (int e = 0; e < nval; ++e) {
+                                if (p.out_mode == OUT_BF16) {
+                                    const uint32_t h = (w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
+                                    reinterpret_cast<uint16_t*>(p.out)[off_r + col + j * 8 + e] = static_cast<uint16_t>(h);
+                                } else if (p.out_mode == OUT_F32) {
+                                    static_cast<float*>(p.out)[off_r + col + j * 4 + e] = __uint_as_float(w4[e]);
+                                } else {
+                                    atomicAdd(static_cast<float*>(p.out) + off_r + col + j * 4 + e, __uint_as_float(w4[e]));
+                                }
+                            }
+                        }
+                    }
+                } else if (row_ok) {
+                    // unaligned buffers: per-thread scalar path
+                    for (int j = 0; j < cvalid; ++j) {
                         float x = v[j];
                         if (has_bias) x += p.bias[col + j];
                         if (has_rb) x += p.rowbias[(gn / p.rb_div) * p.rb_ld + col + j];
@@ -333,7 +396,8 @@ int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
 template <bool A_MN, bool B_MN>
 static int launch_impl(const GemmParams& p, cudaStream_t stream) {
     static bool attr_set = false;
-    const size_t smem = static_cast<size_t>(p.num_stages) * (p.stage_bytes_a + p.stage_bytes_b) + 1024 /*align*/ + 256 /*barriers*/;
+    const size_t smem = static_cast<size_t>(p.num_stages) * (p.stage_bytes_a + p.stage_bytes_b) + 1024 /*align*/ + 256 /*barriers*/ +
+                        kEpilogueStagingBytes;
     auto kern = gemm_tc_kernel<A_MN, B_MN>;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);

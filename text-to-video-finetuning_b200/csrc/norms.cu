@@ -387,9 +387,9 @@ static int gn_block(int C) {
 }
 
 static void gn_chunks(int S, int64_t P, int& chunk_pixels, int& chunks) {
-    // aim for ~4 blocks per SM overall, at least 32 pixels per chunk
+    // aim for ~4 blocks per SM overall; small problems get small chunks (>= 4 pixels) so they still spread over SMs
     const int64_t want = std::max<int64_t>(1, (4 * 148 + S - 1) / S);
-    int64_t cp = std::max<int64_t>(32, (P + want - 1) / want);
+    int64_t cp = std::max<int64_t>(4, (P + want - 1) / want);
     chunk_pixels = int(std::min<int64_t>(cp, P));
     chunks = int((P + chunk_pixels - 1) / chunk_pixels);
 }

@@ -368,16 +368,27 @@ class _Attention(Function):
         ld = p.shape[-1]
         scale = D ** -0.5
         pd = (ld, heads * Lq * ld, Lq * ld)
-        dv = torch.empty_like(v)  # dV = P^T dO
-        prims.bgemm(p, (0,) + pd, do, (0, C, Lq * C, D), dv, (C, Lk * C, D), Lk, D, Lq, Nb, heads, 1.0, 0)
+        # dV = P^T dO and dK = dS^T Q contract over Lq.  For cross-attention (Lq = F*H*W >> Lk = 77) there are only
+        # Nb*heads output tiles, so those two run split-K into an fp32 buffer (red.add) followed by one cast.
+        split = Lq >= 2048 and Lk <= 256
+
+        def over_lq(a_mat, b_mat, like):
+            if not split:
+                out = torch.empty_like(like)
+                prims.bgemm(a_mat, (0,) + pd, b_mat, (0, C, Lq * C, D), out, (C, Lk * C, D), Lk, D, Lq, Nb, heads, 1.0, 0)
+                return out
+            acc = torch.zeros(like.shape, device=like.device, dtype=torch.float32)
+            prims.bgemm(a_mat, (0,) + pd, b_mat, (0, C, Lq * C, D), acc, (C, Lk * C, D), Lk, D, Lq, Nb, heads, 1.0, 2)
+            return prims.cast_f32_bf16(acc)
+
+        dv = over_lq(p, do, v)
         dp = torch.empty((Nb, heads, Lq, ld), device=q.device, dtype=torch.float32)  # dP = dO V^T
         prims.bgemm(do, (1, C, Lq * C, D), v, (1, C, Lk * C, D), dp, pd, Lq, Lk, D, Nb, heads, 1.0, 1)
         ds = prims.softmax_bwd(p, dp, Lk, scale)
         del dp
         dq = torch.empty_like(q)  # dQ = dS K
         prims.bgemm(ds, (1,) + pd, k, (0, C, Lk * C, D), dq, (C, Lq * C, D), Lq, D, Lk, Nb, heads, 1.0, 0)
-        dk = torch.empty_like(k)  # dK = dS^T Q
-        prims.bgemm(ds, (0,) + pd, q, (0, C, Lq * C, D), dk, (C, Lk * C, D), Lk, D, Lq, Nb, heads, 1.0, 0)
+        dk = over_lq(ds, q, k)
         return dq, dk, dv, None
 
 
