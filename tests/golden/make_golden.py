@@ -19,7 +19,7 @@ CASES = {
     "unet_small_f4": dict(cfg=dict(block_out_channels=(32, 64, 64, 64), attention_head_dim=32, cross_attention_dim=32),
                           B=1, F=4, hw=(16, 16), ctx=5, seed=11),
     "unet_small_f1": dict(cfg=dict(block_out_channels=(32, 64, 64, 64), attention_head_dim=32, cross_attention_dim=32),
-                          B=2, F=1, hw=(8, 8), ctx=3, seed=12),
+                          B=2, F=1, hw=(16, 16), ctx=3, seed=12),
 }
 KEEP_FULL = ["conv_in.weight", "down_blocks.0.resnets.0.conv1.weight", "down_blocks.0.temp_convs.0.conv1.2.weight",
              "down_blocks.1.attentions.0.transformer_blocks.0.attn2.to_k.weight", "mid_block.resnets.0.time_emb_proj.weight",
