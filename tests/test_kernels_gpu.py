@@ -171,7 +171,8 @@ def test_latent_boundary_and_loss():
     close(prims.timestep_embedding(tt, 320), ref.timestep_embedding(tt, 320), 1e-2, "timestep emb")
 
 
-@pytest.mark.parametrize("Nb,Lq,Lk,heads,D", [(4, 256, 256, 2, 64), (2, 1024, 77, 5, 64), (3, 64, 64, 1, 512), (2, 100, 36, 3, 64)])
+@pytest.mark.parametrize("Nb,Lq,Lk,heads,D", [(4, 256, 256, 2, 64), (2, 1024, 77, 5, 64), (3, 64, 64, 1, 512), (2, 100, 36, 3, 64),
+                                            (1, 4096, 77, 5, 64)])  # last: cross-attention split-K gradient path
 def test_attention_composite(Nb, Lq, Lk, heads, D):
     """ops.attention (4 tcgen05 batched GEMMs + softmax) vs torch reference, forward and backward."""
     from t2v_b200 import ops

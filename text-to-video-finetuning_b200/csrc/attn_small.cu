@@ -30,15 +30,16 @@ __device__ __forceinline__ int64_t seq_base(const SeqAddr& a, int64_t z, int h, 
 template <int D>
 __device__ __forceinline__ void load_tile(const __nv_bfloat16* __restrict__ g, int64_t base, int64_t stride, int L, float* sm,
                                           int lane) {
-    // D/2 bf16 pairs per token; lane covers pairs lane, lane+32, ...
-    for (int t = 0; t < L; ++t) {
-        const __nv_bfloat162* row = reinterpret_cast<const __nv_bfloat162*>(g + base + t * stride);
-#pragma unroll
-        for (int i = lane; i < D / 2; i += 32) {
-            const float2 f = __bfloat1622float2(row[i]);
-            sm[t * (D + 1) + 2 * i] = f.x;
-            sm[t * (D + 1) + 2 * i + 1] = f.y;
-        }
+    // 16-byte loads: D/8 chunks per token, independent iterations (all loads of a tile are in flight together)
+    constexpr int CPT = D / 8;
+    const int total = L * CPT;
+#pragma unroll 4
+    for (int idx = lane; idx < total; idx += 32) {
+        const int t = idx / CPT, c = idx % CPT;
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(g + base + t * stride) + c);
+        float* dst = sm + t * (D + 1) + c * 8;
+        dst[0] = bf16_lo(q.x); dst[1] = bf16_hi(q.x); dst[2] = bf16_lo(q.y); dst[3] = bf16_hi(q.y);
+        dst[4] = bf16_lo(q.z); dst[5] = bf16_hi(q.z); dst[6] = bf16_lo(q.w); dst[7] = bf16_hi(q.w);
     }
 }
 
@@ -79,17 +80,19 @@ __global__ void attn_small_fwd_kernel(const __nv_bfloat16* __restrict__ q, const
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
             p /= sum;
-            float acc[D / 32];
-#pragma unroll
-            for (int r = 0; r < D / 32; ++r) acc[r] = 0.f;
-            for (int j = 0; j < L; ++j) {
-                const float pj = __shfl_sync(0xffffffffu, p, j);
-#pragma unroll
-                for (int r = 0; r < D / 32; ++r) acc[r] += pj * sv[j * (D + 1) + lane + 32 * r];
+            if (D == 64) {  // lane owns dims (2*lane, 2*lane+1): one coalesced 128-byte row store per query
+                float a0 = 0.f, a1 = 0.f;
+                for (int j = 0; j < L; ++j) {
+                    const float pj = __shfl_sync(0xffffffffu, p, j);
+                    a0 += pj * sv[j * (D + 1) + 2 * lane];
+                    a1 += pj * sv[j * (D + 1) + 2 * lane + 1];
+                }
+                reinterpret_cast<__nv_bfloat162*>(o + base + i * a.seq_stride)[lane] = __floats2bfloat162_rn(a0, a1);
+            } else {
+                float a0 = 0.f;
+                for (int j = 0; j < L; ++j) a0 += __shfl_sync(0xffffffffu, p, j) * sv[j * (D + 1) + lane];
+                o[base + i * a.seq_stride + lane] = __float2bfloat16_rn(a0);
             }
-            __nv_bfloat16* orow = o + base + i * a.seq_stride;
-#pragma unroll
-            for (int r = 0; r < D / 32; ++r) orow[lane + 32 * r] = __float2bfloat16_rn(acc[r]);
         }
     }
 }
@@ -152,25 +155,29 @@ __global__ void attn_small_bwd_kernel(const __nv_bfloat16* __restrict__ q, const
         }
         __syncwarp();
         for (int i = 0; i < L; ++i) {
-            float aq[D / 32], ak[D / 32], av[D / 32];
+            constexpr int NP = D == 64 ? 2 : 1;          // dims per lane: (2*lane, 2*lane+1) for D=64, lane for D=32
+            float aq[NP], ak[NP], av[NP];
 #pragma unroll
-            for (int r = 0; r < D / 32; ++r) aq[r] = ak[r] = av[r] = 0.f;
+            for (int r = 0; r < NP; ++r) aq[r] = ak[r] = av[r] = 0.f;
             for (int j = 0; j < L; ++j) {
                 const float ds_ij = ss[i * L + j], ds_ji = ss[j * L + i], p_ji = sp[j * L + i];
 #pragma unroll
-                for (int r = 0; r < D / 32; ++r) {
-                    const int d = lane + 32 * r;
+                for (int r = 0; r < NP; ++r) {
+                    const int d = NP * lane + r;
                     aq[r] += ds_ij * sk[j * (D + 1) + d];   // dQ_i = sum_j dS_ij K_j
                     ak[r] += ds_ji * sq[j * (D + 1) + d];   // dK_i = sum_j dS_ji Q_j
                     av[r] += p_ji * sd[j * (D + 1) + d];    // dV_i = sum_j P_ji dO_j
                 }
             }
             const int64_t off = base + i * a.seq_stride;
-#pragma unroll
-            for (int r = 0; r < D / 32; ++r) {
-                dq[off + lane + 32 * r] = __float2bfloat16_rn(aq[r]);
-                dk[off + lane + 32 * r] = __float2bfloat16_rn(ak[r]);
-                dv[off + lane + 32 * r] = __float2bfloat16_rn(av[r]);
+            if (D == 64) {
+                reinterpret_cast<__nv_bfloat162*>(dq + off)[lane] = __floats2bfloat162_rn(aq[0], aq[NP - 1]);
+                reinterpret_cast<__nv_bfloat162*>(dk + off)[lane] = __floats2bfloat162_rn(ak[0], ak[NP - 1]);
+                reinterpret_cast<__nv_bfloat162*>(dv + off)[lane] = __floats2bfloat162_rn(av[0], av[NP - 1]);
+            } else {
+                dq[off + lane] = __float2bfloat16_rn(aq[0]);
+                dk[off + lane] = __float2bfloat16_rn(ak[0]);
+                dv[off + lane] = __float2bfloat16_rn(av[0]);
             }
         }
     }

@@ -4,6 +4,7 @@
 #include "gemm_tc.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 using namespace t2v;
@@ -34,7 +35,13 @@ Box3 choose_pixel_box(int prod, int W, int H, int N) {
 }
 
 // UMMA N for a problem with `row_tiles` row tiles and `ncols` columns: fewest waves, then least padding.
+int env_int(const char* name) {
+    const char* v = std::getenv(name);
+    return v ? std::atoi(v) : 0;
+}
+
 int choose_block_n(int64_t row_tiles, int ncols, bool mn_major_b) {
+    if (const int forced = env_int("T2V_FORCE_BN")) return forced;  // tuning / profiling hook
     const int sms = device_sm_count();
     int best = 16;
     double best_cost = 1e30;
@@ -76,9 +83,23 @@ void finish_common(GemmParams& p, bool b_mn) {
     p.stage_bytes_b = b_mn ? ((p.block_n + 63) / 64) * 8192 : p.block_n * 128;
     const int budget = 232448 - 1024 - 256 - kEpilogueStagingBytes;
     p.num_stages = std::min<int>(kMaxStages, budget / (p.stage_bytes_a + p.stage_bytes_b));
+    if (const int forced = env_int("T2V_FORCE_STAGES")) p.num_stages = std::min(p.num_stages, forced);
     int64_t tiles = 1;
     for (int i = 0; i < 6; ++i) tiles *= p.tdim[i];
     p.num_tiles = static_cast<int32_t>(tiles);
+    for (int i = 0; i < 6; ++i) {  // q = umulhi(n, mul) >> shr for 0 <= n < 2^31 (CUTLASS FastDivmod construction)
+        const uint32_t d = static_cast<uint32_t>(p.tdim[i]);
+        if (d <= 1) {
+            p.tdiv_mul[i] = 0;
+            p.tdiv_shr[i] = 0;
+            continue;
+        }
+        uint32_t lg = 0;
+        while ((1ull << lg) < d) ++lg;
+        const uint32_t pw = 31 + lg;
+        p.tdiv_mul[i] = static_cast<uint32_t>(((1ull << pw) + d - 1) / d);
+        p.tdiv_shr[i] = pw - 32;
+    }
     p.kb_total = p.kdim[0] * p.kdim[1] * p.kdim[2];
 }
 

@@ -18,18 +18,24 @@ struct TileVars {
     int32_t t[6];
 };
 
+// tile id -> six mixed-radix digits, with host-precomputed magic numbers (q = umulhi(n, mul) >> shr; n < 2^31)
 __device__ __forceinline__ void decompose_tile(const GemmParams& p, int32_t tile, TileVars& tv) {
+    uint32_t n = static_cast<uint32_t>(tile);
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-        const int32_t d = p.tdim[i];
-        tv.t[i] = tile % d;
-        tile /= d;
+        const uint32_t d = static_cast<uint32_t>(p.tdim[i]);
+        const uint32_t q = d == 1u ? n : (__umulhi(n, p.tdiv_mul[i]) >> p.tdiv_shr[i]);
+        tv.t[i] = static_cast<int32_t>(n - q * d);
+        n = q;
     }
 }
 
 __device__ __forceinline__ void k_range(const GemmParams& p, const TileVars& tv, int32_t& kb0, int32_t& kb1) {
     if (p.ksplit_var >= 0) {
-        kb0 = tv.t[p.ksplit_var] * p.kb_per_split;
+        int32_t sv = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) sv = (i == p.ksplit_var) ? tv.t[i] : sv;
+        kb0 = sv * p.kb_per_split;
         kb1 = min(p.kb_total, kb0 + p.kb_per_split);
     } else {
         kb0 = 0;
@@ -37,21 +43,20 @@ __device__ __forceinline__ void k_range(const GemmParams& p, const TileVars& tv,
     }
 }
 
-__device__ __forceinline__ void tile_coords(const TmaOperand& op, const TileVars& tv, int32_t* c) {
+// TMA coordinates of one operand at (tile, k-loop digits kv)
+__device__ __forceinline__ void operand_coords(const TmaOperand& op, const TileVars& tv, const int32_t* kv, int32_t* c) {
 #pragma unroll
     for (int d = 0; d < 5; ++d) {
         int32_t v = op.base[d];
 #pragma unroll
         for (int i = 0; i < 6; ++i) v += tv.t[i] * op.tcoef[d][i];
+        v += kv[0] * op.kcoef[d][0] + kv[1] * op.kcoef[d][1] + kv[2] * op.kcoef[d][2];
         c[d] = v;
     }
 }
 
-__device__ __forceinline__ void issue_operand(const TmaOperand& op, const int32_t* tile_c, const int32_t* kv,
-                                              uint8_t* smem_dst, uint64_t* bar) {
-    int32_t c[5];
-#pragma unroll
-    for (int d = 0; d < 5; ++d) c[d] = tile_c[d] + kv[0] * op.kcoef[d][0] + kv[1] * op.kcoef[d][1] + kv[2] * op.kcoef[d][2];
+__device__ __forceinline__ void issue_boxes(const TmaOperand& op, const int32_t* c_in, uint8_t* smem_dst, uint64_t* bar) {
+    int32_t c[5] = {c_in[0], c_in[1], c_in[2], c_in[3], c_in[4]};
     for (int b = 0; b < op.nbox; ++b) {  // boxes of an MN-major operand always advance along dimension 0
         tma_load(op.rank, smem_dst + b * op.box_bytes, &op.map, bar, c);
         c[0] += op.box_step;
@@ -103,27 +108,36 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
             for (int32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 TileVars tv;
                 decompose_tile(p, tile, tv);
-                int32_t ca[5], cb[5];
-                tile_coords(p.a, tv, ca);
-                tile_coords(p.b, tv, cb);
                 int32_t kb0, kb1;
                 k_range(p, tv, kb0, kb1);
-                // k-loop variables advance as a mixed-radix counter (no div/mod per k-block)
+                // k-loop digits advance as a mixed-radix counter; coordinates are updated incrementally (adds only) and
+                // recomputed from scratch only when the fastest digit wraps
                 int32_t kv[3];
                 kv[0] = kb0 % p.kdim[0];
                 kv[1] = (kb0 / p.kdim[0]) % p.kdim[1];
                 kv[2] = kb0 / (p.kdim[0] * p.kdim[1]);
+                int32_t ca[5], cb[5];
+                operand_coords(p.a, tv, kv, ca);
+                operand_coords(p.b, tv, kv, cb);
                 for (int32_t kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], tx_bytes);
-                    issue_operand(p.a, ca, kv, smem_a + static_cast<size_t>(stage) * p.stage_bytes_a, &full_bar[stage]);
-                    issue_operand(p.b, cb, kv, smem_b + static_cast<size_t>(stage) * p.stage_bytes_b, &full_bar[stage]);
-                    if (++kv[0] == p.kdim[0]) {
+                    issue_boxes(p.a, ca, smem_a + static_cast<size_t>(stage) * p.stage_bytes_a, &full_bar[stage]);
+                    issue_boxes(p.b, cb, smem_b + static_cast<size_t>(stage) * p.stage_bytes_b, &full_bar[stage]);
+                    if (++kv[0] < p.kdim[0]) {
+#pragma unroll
+                        for (int d = 0; d < 5; ++d) {
+                            ca[d] += p.a.kcoef[d][0];
+                            cb[d] += p.b.kcoef[d][0];
+                        }
+                    } else {
                         kv[0] = 0;
                         if (++kv[1] == p.kdim[1]) {
                             kv[1] = 0;
                             ++kv[2];
                         }
+                        operand_coords(p.a, tv, kv, ca);
+                        operand_coords(p.b, tv, kv, cb);
                     }
                     if (++stage == static_cast<uint32_t>(S)) {
                         stage = 0;

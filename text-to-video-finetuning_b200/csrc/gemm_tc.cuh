@@ -51,6 +51,8 @@ enum EpiFlags : int32_t {
 struct alignas(64) GemmParams {
     TmaOperand a, b;
     int32_t tdim[6];       // tile grid, t[0] fastest
+    uint32_t tdiv_mul[6];  // magic numbers for division by tdim[i]
+    uint32_t tdiv_shr[6];
     int32_t kdim[3];       // k-block grid, k[0] fastest
     int32_t num_tiles;
     int32_t kb_total;
