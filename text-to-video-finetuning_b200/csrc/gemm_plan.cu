@@ -40,25 +40,76 @@ int env_int(const char* name) {
     return v ? std::atoi(v) : 0;
 }
 
-int choose_block_n(int64_t row_tiles, int ncols, bool mn_major_b) {
-    if (const int forced = env_int("T2V_FORCE_BN")) return forced;  // tuning / profiling hook
+struct Tiling {
+    int bn;        // UMMA N
+    int mh;        // 128-row halves per tile (1 or 2)
+    int pair_var;  // tile variable (1..3) the halves pair up, -1 if mh == 1
+};
+
+// Picks (block_n, row halves) with a small roofline model of the kernel.  Measured on B200 (profiles/): the main loop is
+// bound by the chip-wide L2->SM operand bandwidth (~5200 B/clk over all active CTAs) before it is bound by tcgen05
+// (2*bn clk per 64-deep k-block and 128-row half), so wide tiles and 256-row tiles (B shared by two accumulators) win
+// whenever enough tiles remain to fill the 148 SMs.
+//   row_dims[0..2] = tile counts of tile variables 1..3 (unpaired), extra = product of the remaining tile variables.
+Tiling choose_tiling(const int row_dims[3], int ncols, bool mn_major_b, int kblocks, int64_t extra, bool allow_pair) {
     const int sms = device_sm_count();
-    int best = 16;
+    const int forced_bn = env_int("T2V_FORCE_BN"), forced_mh = env_int("T2V_FORCE_MH");
+    Tiling best{16, 1, -1};
     double best_cost = 1e30;
-    for (int bn = 256; bn >= 16; bn -= 16) {
-        if (bn > 16 && bn - 16 >= ncols) continue;  // strictly more padding than needed
-        const int64_t col_tiles = (ncols + bn - 1) / bn;
-        const int64_t tiles = row_tiles * col_tiles;
-        const int64_t waves = (tiles + sms - 1) / sms;
-        // per-tile time ~ max(MMA time ~ bn, A-operand smem fill floor)
-        double cost = double(waves) * std::max(bn, 96);
-        if (mn_major_b) cost *= 1.0 + 0.02 * ((64 - bn % 64) % 64) / 64.0;  // unused part of the last 64-wide box
-        if (cost < best_cost - 1e-9) {
-            best_cost = cost;
-            best = bn;
+    for (int mh = 1; mh <= 2; ++mh) {
+        if (forced_mh && mh != forced_mh) continue;
+        int pv = -1;
+        int64_t m_tiles = int64_t(row_dims[0]) * row_dims[1] * row_dims[2];
+        if (mh == 2) {
+            if (!allow_pair) continue;
+            double best_waste = 1e30;
+            for (int v = 2; v >= 0; --v) {
+                if (row_dims[v] < 2) continue;
+                const double waste = double((row_dims[v] + 1) / 2 * 2) / row_dims[v];
+                if (waste < best_waste - 1e-9) {
+                    best_waste = waste;
+                    pv = v + 1;
+                }
+            }
+            if (pv < 0) continue;
+            m_tiles = m_tiles / row_dims[pv - 1] * ((row_dims[pv - 1] + 1) / 2);
+        }
+        for (int bn = 256; bn >= 16; bn -= 16) {
+            if (forced_bn && bn != forced_bn) continue;
+            if (bn > 16 && bn - 16 >= ncols) continue;  // strictly more padding than needed
+            const int b_bytes = mn_major_b ? ((bn + 63) / 64) * 8192 : bn * 128;
+            const int stage_bytes = mh * kBlockM * 128 + b_bytes;
+            const int budget = 232448 - 1024 - 256 - kEpilogueStagingBytes;
+            if (budget / stage_bytes < 3) continue;
+            const int64_t tiles = m_tiles * ((ncols + bn - 1) / bn) * extra;
+            const int64_t waves = (tiles + sms - 1) / sms;
+            const double active = double(std::min<int64_t>(tiles, sms));
+            const double t_kb = std::max({double(mh) * 2.0 * bn, stage_bytes * active / 5200.0, 260.0});
+            const bool overlap = mh == 1 || bn <= 128;  // two TMEM accumulator stages available
+            const double t_epi = (bn / 32.0 + 1.0) * 450.0 * (mh == 2 ? 1.0 : 0.5) * (overlap ? 0.35 : 1.0);
+            const double cost = double(waves) * (kblocks * t_kb + t_epi + 1800.0);
+            if (cost < best_cost - 1e-9) {
+                best_cost = cost;
+                best = Tiling{bn, mh, pv};
+            }
         }
     }
     return best;
+}
+
+void apply_tiling(GemmParams& p, const Tiling& t) {
+    p.block_n = t.bn;
+    p.mh = t.mh;
+    p.pair_var = t.pair_var;
+    if (t.mh == 2) {
+        p.tdim[t.pair_var] = (p.tdim[t.pair_var] + 1) / 2;
+        p.acc_half_cols = t.bn <= 128 ? 128 : 256;
+        p.acc_stage_cols = 2 * p.acc_half_cols;
+    } else {
+        p.acc_half_cols = 0;
+        p.acc_stage_cols = 256;
+    }
+    p.nacc = 512 / p.acc_stage_cols;
 }
 
 // Split-K factor for accumulate-mode problems: minimise  waves(base_tiles * s) * (k-blocks per split * T_kblock + T_epilogue).
@@ -79,7 +130,7 @@ int choose_splits(int64_t base_tiles, int kb_total) {
 }
 
 void finish_common(GemmParams& p, bool b_mn) {
-    p.stage_bytes_a = kBlockM * 128;
+    p.stage_bytes_a = p.mh * kBlockM * 128;
     p.stage_bytes_b = b_mn ? ((p.block_n + 63) / 64) * 8192 : p.block_n * 128;
     const int budget = 232448 - 1024 - 256 - kEpilogueStagingBytes;
     p.num_stages = std::min<int>(kMaxStages, budget / (p.stage_bytes_a + p.stage_bytes_b));
@@ -147,9 +198,6 @@ int t2v_conv_fwd(const void* x, const void* w, void* y, int32_t N, int32_t H, in
     GemmParams p;
     std::memset(&p, 0, sizeof(p));
     const Box3 bx = choose_pixel_box(kBlockM, Wo, Ho, N);
-    const int64_t row_tiles = int64_t((Wo + bx.w - 1) / bx.w) * ((Ho + bx.h - 1) / bx.h) * ((N + bx.n - 1) / bx.n);
-    p.block_n = choose_block_n(row_tiles, Cout, false);
-    p.tdim[0] = (Cout + p.block_n - 1) / p.block_n;
     p.tdim[1] = (Wo + bx.w - 1) / bx.w;
     p.tdim[2] = (Ho + bx.h - 1) / bx.h;
     p.tdim[3] = (N + bx.n - 1) / bx.n;
@@ -158,6 +206,11 @@ int t2v_conv_fwd(const void* x, const void* w, void* y, int32_t N, int32_t H, in
     p.kdim[1] = KW;
     p.kdim[2] = KH;
     p.ksplit_var = -1;
+    {
+        const int rd[3] = {p.tdim[1], p.tdim[2], p.tdim[3]};
+        apply_tiling(p, choose_tiling(rd, Cout, false, p.kdim[0] * KW * KH, 1, true));
+    }
+    p.tdim[0] = (Cout + p.block_n - 1) / p.block_n;
     // A: activations, K-major pixel box with tap shifts
     {
         TmaOperand& a = p.a;
@@ -212,9 +265,6 @@ int t2v_conv_dgrad(const void* dy, const void* w, void* dx, int32_t N, int32_t H
             GemmParams p;
             std::memset(&p, 0, sizeof(p));
             const Box3 bx = choose_pixel_box(kBlockM, Wc, Hc, N);
-            const int64_t row_tiles = int64_t((Wc + bx.w - 1) / bx.w) * ((Hc + bx.h - 1) / bx.h) * ((N + bx.n - 1) / bx.n);
-            p.block_n = choose_block_n(row_tiles, Cin, true);
-            p.tdim[0] = (Cin + p.block_n - 1) / p.block_n;
             p.tdim[1] = (Wc + bx.w - 1) / bx.w;
             p.tdim[2] = (Hc + bx.h - 1) / bx.h;
             p.tdim[3] = (N + bx.n - 1) / bx.n;
@@ -223,6 +273,11 @@ int t2v_conv_dgrad(const void* dy, const void* w, void* dx, int32_t N, int32_t H
             p.kdim[1] = ntw;
             p.kdim[2] = nth;
             p.ksplit_var = -1;
+            {
+                const int rd[3] = {p.tdim[1], p.tdim[2], p.tdim[3]};
+                apply_tiling(p, choose_tiling(rd, Cin, true, p.kdim[0] * ntw * nth, 1, true));
+            }
+            p.tdim[0] = (Cin + p.block_n - 1) / p.block_n;
             {
                 TmaOperand& a = p.a;  // dy, K-major (K = Cout), pixel box shifted against the tap
                 const uint64_t dims[4] = {uint64_t(Cout), uint64_t(Wo), uint64_t(Ho), uint64_t(N)};
@@ -272,16 +327,22 @@ int t2v_conv_wgrad(const void* x, const void* dy, float* dw, int32_t N, int32_t 
     GemmParams p;
     std::memset(&p, 0, sizeof(p));
     const Box3 kx = choose_pixel_box(kBlockK, Wo, Ho, N);  // 64 output pixels per k-block
-    const int64_t row_tiles = int64_t((Cout + kBlockM - 1) / kBlockM) * KH * KW;
-    p.block_n = choose_block_n(row_tiles, Cin, true);
     p.kdim[0] = (Wo + kx.w - 1) / kx.w;
     p.kdim[1] = (Ho + kx.h - 1) / kx.h;
     p.kdim[2] = (N + kx.n - 1) / kx.n;
     const int kb_total = p.kdim[0] * p.kdim[1] * p.kdim[2];
-    p.tdim[0] = (Cin + p.block_n - 1) / p.block_n;
     p.tdim[1] = (Cout + kBlockM - 1) / kBlockM;
     p.tdim[2] = KW;
     p.tdim[3] = KH;
+    {
+        // only the Cout tiles (variable 1) can pair up; taps and k-splits multiply the tile count.  The split factor is
+        // chosen afterwards, so model the main loop with the k-blocks a ~1-wave split would leave per tile.
+        const int rd[3] = {p.tdim[1], 1, 1};
+        const int64_t taps = int64_t(KH) * KW;
+        const int kb_guess = std::max<int>(4, int(std::min<int64_t>(kb_total, kb_total * taps * p.tdim[1] * ((Cin + 159) / 160) / device_sm_count())));
+        apply_tiling(p, choose_tiling(rd, Cin, true, kb_guess, taps, true));
+    }
+    p.tdim[0] = (Cin + p.block_n - 1) / p.block_n;
     const int64_t base_tiles = int64_t(p.tdim[0]) * p.tdim[1] * KW * KH;
     int splits = choose_splits(base_tiles, kb_total);
     p.kb_per_split = (kb_total + splits - 1) / splits;
@@ -330,16 +391,18 @@ int t2v_bgemm(const T2VMat* A, const T2VMat* B, void* C, int64_t ldc, int64_t c_
     const bool a_mn = !A->kmajor, b_mn = !B->kmajor;
     GemmParams p;
     std::memset(&p, 0, sizeof(p));
-    const int64_t row_tiles = int64_t((M + kBlockM - 1) / kBlockM) * Z1 * Z2;
-    p.block_n = choose_block_n(row_tiles, N, b_mn);
     p.kdim[0] = (K + kBlockK - 1) / kBlockK;
     p.kdim[1] = p.kdim[2] = 1;
-    p.tdim[0] = (N + p.block_n - 1) / p.block_n;
     p.tdim[1] = (M + kBlockM - 1) / kBlockM;
     p.tdim[2] = 1;
     p.tdim[3] = 1;
     p.tdim[4] = Z2;
     p.tdim[5] = Z1;
+    {
+        const int rd[3] = {p.tdim[1], 1, 1};
+        apply_tiling(p, choose_tiling(rd, N, b_mn, out_mode == OUT_F32_RED ? std::max(2, p.kdim[0] / 4) : p.kdim[0], int64_t(Z1) * Z2, true));
+    }
+    p.tdim[0] = (N + p.block_n - 1) / p.block_n;
     p.ksplit_var = -1;
     int splits = 1;
     if (out_mode == OUT_F32_RED) {

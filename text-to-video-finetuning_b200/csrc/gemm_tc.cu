@@ -28,6 +28,10 @@ __device__ __forceinline__ void decompose_tile(const GemmParams& p, int32_t tile
         tv.t[i] = static_cast<int32_t>(n - q * d);
         n = q;
     }
+    if (p.mh == 2) {  // 256-row tiles: t[pair_var] counts PAIRS of row tiles; half h of the tile is row tile 2*t + h
+#pragma unroll
+        for (int i = 0; i < 6; ++i) tv.t[i] = (i == p.pair_var) ? tv.t[i] * 2 : tv.t[i];
+    }
 }
 
 __device__ __forceinline__ void k_range(const GemmParams& p, const TileVars& tv, int32_t& kb0, int32_t& kb1) {
@@ -104,7 +108,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
         // ------------------------------------------------------------------ TMA producer
         if (elect_one()) {
             uint32_t stage = 0, phase = 0;
-            const uint32_t tx_bytes = p.stage_bytes_a + p.stage_bytes_b;
+            const uint32_t tx_bytes = p.stage_bytes_a + p.stage_bytes_b;  // stage_bytes_a covers both row halves when mh == 2
+            int32_t half_delta[5];
+#pragma unroll
+            for (int d = 0; d < 5; ++d) {
+                int32_t v = 0;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) v = (i == p.pair_var) ? p.a.tcoef[d][i] : v;
+                half_delta[d] = v;
+            }
             for (int32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 TileVars tv;
                 decompose_tile(p, tile, tv);
@@ -123,6 +135,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], tx_bytes);
                     issue_boxes(p.a, ca, smem_a + static_cast<size_t>(stage) * p.stage_bytes_a, &full_bar[stage]);
+                    if (p.mh == 2) {
+                        int32_t c1[5];
+#pragma unroll
+                        for (int d = 0; d < 5; ++d) c1[d] = ca[d] + half_delta[d];
+                        issue_boxes(p.a, c1, smem_a + static_cast<size_t>(stage) * p.stage_bytes_a + kBlockM * 128, &full_bar[stage]);
+                    }
                     issue_boxes(p.b, cb, smem_b + static_cast<size_t>(stage) * p.stage_bytes_b, &full_bar[stage]);
                     if (++kv[0] < p.kdim[0]) {
 #pragma unroll
@@ -162,11 +180,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                 decompose_tile(p, tile, tv);
                 int32_t kb0, kb1;
                 k_range(p, tv, kb0, kb1);
-                const uint32_t as = it & 1u;
-                const uint32_t aphase = (it >> 1) & 1u;
+                const uint32_t as = p.nacc == 2 ? (it & 1u) : 0u;
+                const uint32_t aphase = p.nacc == 2 ? ((it >> 1) & 1u) : (it & 1u);
                 mbar_wait(&acc_empty[as], aphase ^ 1);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * 256u;
+                const uint32_t tmem_d = tmem_base + as * p.acc_stage_cols;
                 for (int32_t kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -175,6 +193,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
 #pragma unroll
                     for (uint32_t k = 0; k < kBlockK / 16; ++k) {
                         umma_f16(tmem_d, da + k * a_kstep, db + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        if (p.mh == 2)  // second 128-row half: same B tile, A half 1 (16 KB further), accumulator half 1
+                            umma_f16(tmem_d + p.acc_half_cols, da + ((kBlockM * 128) >> 4) + k * a_kstep, db + k * b_kstep, idesc,
+                                     (kb > kb0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
                     if (++stage == static_cast<uint32_t>(S)) {
@@ -200,8 +221,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
         const bool has_bias = p.flags & EPI_BIAS, has_rb = p.flags & EPI_ROWBIAS, has_res = p.flags & EPI_RESIDUAL;
         const bool vec = p.flags & EPI_VEC;
         const int nchunks = (p.block_n + 31) >> 5;
-        const int c_begin = grp == 0 ? 0 : (nchunks + 1) >> 1;
-        const int c_end = grp == 0 ? (nchunks + 1) >> 1 : nchunks;
+        // mh == 1: the two warp groups split the columns of one 128-row accumulator;  mh == 2: group g drains row half g
+        const int c_begin = (p.mh == 2 || grp == 0) ? 0 : (nchunks + 1) >> 1;
+        const int c_end = p.mh == 2 ? nchunks : (grp == 0 ? (nchunks + 1) >> 1 : nchunks);
         uint8_t* stg = reinterpret_cast<uint8_t*>(tmem_slot + 4) + ew * 4096u;  // 32 rows x <=128 B
         const int esz = p.out_mode == OUT_BF16 ? 2 : 4;
         const int cpr = esz * 2;  // 16-byte chunks per 32-column row: 4 (bf16) or 8 (fp32)
@@ -211,17 +233,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
         for (int32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             TileVars tv;
             decompose_tile(p, tile, tv);
+            if (p.mh == 2 && grp == 1) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) tv.t[i] += (i == p.pair_var) ? 1 : 0;
+            }
             const int32_t gw = tv.t[1] * p.bw + rw, gh = tv.t[2] * p.bh + rh, gn = tv.t[3] * p.bn + rn;
             const bool row_ok = (rn < p.bn) && gw < p.W && gh < p.H && gn < p.N;
             int64_t off = gw * p.ldw + gh * p.ldh + gn * p.ldn;
 #pragma unroll
             for (int i = 0; i < 6; ++i) off += tv.t[i] * p.otc[i];
             const int32_t col0 = tv.t[0] * p.block_n;
-            const uint32_t as = it & 1u;
-            const uint32_t aphase = (it >> 1) & 1u;
+            const uint32_t as = p.nacc == 2 ? (it & 1u) : 0u;
+            const uint32_t aphase = p.nacc == 2 ? ((it >> 1) & 1u) : (it & 1u);
             mbar_wait(&acc_full[as], aphase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + as * 256u;
+            const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + as * p.acc_stage_cols + (p.mh == 2 ? grp * p.acc_half_cols : 0u);
             for (int ch = c_begin; ch < c_end; ++ch) {
                 const int32_t col = col0 + ch * 32;
                 const int32_t cvalid = min(32, min(p.block_n - ch * 32, p.ncols - col));  // valid columns of this chunk

@@ -61,6 +61,13 @@ struct alignas(64) GemmParams {
     int32_t block_n;       // UMMA N (multiple of 16, <= 256)
     int32_t num_stages;
     int32_t stage_bytes_a, stage_bytes_b;
+    // 256-row tiles: two 128-row halves (consecutive values of tile variable `pair_var`) share one B tile per k-block,
+    // halving the weight-operand traffic from L2 per MAC; each half has its own TMEM accumulator.
+    int32_t mh;              // 1 or 2 row halves per tile
+    int32_t pair_var;        // tile variable paired by the halves (its tdim counts pairs), -1 when mh == 1
+    uint32_t nacc;           // accumulator stages in TMEM (2 = epilogue overlaps the next tile's main loop)
+    uint32_t acc_stage_cols; // TMEM columns per accumulator stage
+    uint32_t acc_half_cols;  // TMEM column offset of row half 1 inside a stage
     // epilogue: accumulator row r of a tile maps to the "pixel box" (w,h,n) = (r % bw, r / bw % bh, r / (bw*bh))
     // at global position (t[1]*bw + w, t[2]*bh + h, t[3]*bn + n); column c maps to t[0]*block_n + c.
     int32_t bw, bh, bn;
