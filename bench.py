@@ -200,6 +200,7 @@ def main():
     # launches per step, counted on an eager step
     eager = S.DataParallelStep(unet, abar, passes=1, use_graph=False, adopt=False)
     eager.arena = step.arena
+    eager.sync_gradients = False  # profiling passes below run on their own rank: no collective
     n0 = native.launch_count()
     eager(*devin)
     torch.cuda.synchronize()

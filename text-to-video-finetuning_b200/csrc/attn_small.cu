@@ -154,30 +154,53 @@ __global__ void attn_small_bwd_kernel(const __nv_bfloat16* __restrict__ q, const
             }
         }
         __syncwarp();
-        for (int i = 0; i < L; ++i) {
-            constexpr int NP = D == 64 ? 2 : 1;          // dims per lane: (2*lane, 2*lane+1) for D=64, lane for D=32
-            float aq[NP], ak[NP], av[NP];
+        // Phase 2: lane owns NP adjacent head dims of every row.  Rows are cached in registers in slabs of 8 keys so the
+        // inner loops are broadcast-scalar x register FMAs (no bank-conflicted shared-memory reads).
+        constexpr int NP = D == 64 ? 2 : 1;
+        constexpr int SLAB = 8;
+        for (int i0 = 0; i0 < L; i0 += SLAB) {
+            float aq[SLAB][NP], ak[SLAB][NP], av[SLAB][NP];
 #pragma unroll
-            for (int r = 0; r < NP; ++r) aq[r] = ak[r] = av[r] = 0.f;
+            for (int ii = 0; ii < SLAB; ++ii)
+#pragma unroll
+                for (int r = 0; r < NP; ++r) aq[ii][r] = ak[ii][r] = av[ii][r] = 0.f;
             for (int j = 0; j < L; ++j) {
-                const float ds_ij = ss[i * L + j], ds_ji = ss[j * L + i], p_ji = sp[j * L + i];
+                float kj[NP], qj[NP], dj[NP];
 #pragma unroll
                 for (int r = 0; r < NP; ++r) {
                     const int d = NP * lane + r;
-                    aq[r] += ds_ij * sk[j * (D + 1) + d];   // dQ_i = sum_j dS_ij K_j
-                    ak[r] += ds_ji * sq[j * (D + 1) + d];   // dK_i = sum_j dS_ji Q_j
-                    av[r] += p_ji * sd[j * (D + 1) + d];    // dV_i = sum_j P_ji dO_j
+                    kj[r] = sk[j * (D + 1) + d];
+                    qj[r] = sq[j * (D + 1) + d];
+                    dj[r] = sd[j * (D + 1) + d];
+                }
+#pragma unroll
+                for (int ii = 0; ii < SLAB; ++ii) {
+                    const int i = i0 + ii;
+                    if (i < L) {
+                        const float ds_ij = ss[i * L + j], ds_ji = ss[j * L + i], p_ji = sp[j * L + i];
+#pragma unroll
+                        for (int r = 0; r < NP; ++r) {
+                            aq[ii][r] += ds_ij * kj[r];   // dQ_i = sum_j dS_ij K_j
+                            ak[ii][r] += ds_ji * qj[r];   // dK_i = sum_j dS_ji Q_j
+                            av[ii][r] += p_ji * dj[r];    // dV_i = sum_j P_ji dO_j
+                        }
+                    }
                 }
             }
-            const int64_t off = base + i * a.seq_stride;
-            if (D == 64) {
-                reinterpret_cast<__nv_bfloat162*>(dq + off)[lane] = __floats2bfloat162_rn(aq[0], aq[NP - 1]);
-                reinterpret_cast<__nv_bfloat162*>(dk + off)[lane] = __floats2bfloat162_rn(ak[0], ak[NP - 1]);
-                reinterpret_cast<__nv_bfloat162*>(dv + off)[lane] = __floats2bfloat162_rn(av[0], av[NP - 1]);
-            } else {
-                dq[off + lane] = __float2bfloat16_rn(aq[0]);
-                dk[off + lane] = __float2bfloat16_rn(ak[0]);
-                dv[off + lane] = __float2bfloat16_rn(av[0]);
+#pragma unroll
+            for (int ii = 0; ii < SLAB; ++ii) {
+                const int i = i0 + ii;
+                if (i >= L) break;
+                const int64_t off = base + i * a.seq_stride;
+                if (D == 64) {
+                    reinterpret_cast<__nv_bfloat162*>(dq + off)[lane] = __floats2bfloat162_rn(aq[ii][0], aq[ii][NP - 1]);
+                    reinterpret_cast<__nv_bfloat162*>(dk + off)[lane] = __floats2bfloat162_rn(ak[ii][0], ak[ii][NP - 1]);
+                    reinterpret_cast<__nv_bfloat162*>(dv + off)[lane] = __floats2bfloat162_rn(av[ii][0], av[ii][NP - 1]);
+                } else {
+                    dq[off + lane] = __float2bfloat16_rn(aq[ii][0]);
+                    dk[off + lane] = __float2bfloat16_rn(ak[ii][0]);
+                    dv[off + lane] = __float2bfloat16_rn(av[ii][0]);
+                }
             }
         }
     }

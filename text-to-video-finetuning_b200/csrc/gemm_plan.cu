@@ -84,7 +84,9 @@ Tiling choose_tiling(const int row_dims[3], int ncols, bool mn_major_b, int kblo
             const int64_t tiles = m_tiles * ((ncols + bn - 1) / bn) * extra;
             const int64_t waves = (tiles + sms - 1) / sms;
             const double active = double(std::min<int64_t>(tiles, sms));
-            const double t_kb = std::max({double(mh) * 2.0 * bn, stage_bytes * active / 5200.0, 260.0});
+            // three ceilings per k-block: tcgen05 issue rate, chip-wide L2->SM bandwidth shared by the active CTAs, and
+            // the per-SM shared-memory fill rate (~48 B/clk measured)
+            const double t_kb = std::max({double(mh) * 2.0 * bn, stage_bytes * active / 5200.0, stage_bytes / 48.0, 260.0});
             const bool overlap = mh == 1 || bn <= 128;  // two TMEM accumulator stages available
             const double t_epi = (bn / 32.0 + 1.0) * 450.0 * (mh == 2 ? 1.0 : 0.5) * (overlap ? 0.35 : 1.0);
             const double cost = double(waves) * (kblocks * t_kb + t_epi + 1800.0);

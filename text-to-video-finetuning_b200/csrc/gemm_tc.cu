@@ -67,6 +67,184 @@ __device__ __forceinline__ void issue_boxes(const TmaOperand& op, const int32_t*
     }
 }
 
+// Epilogue of one CTA (warps 2..9).  mh == 1: the two groups of four warps split the accumulator columns; mh == 2: group g
+// drains row half g.  Within a group warp w owns TMEM lanes 32*(w%4)..+31, i.e. thread <-> output row.  Output rows are
+// strided in global memory, so every 32-column chunk goes through a per-warp swizzled staging tile and is moved with
+// 16 bytes per lane covering whole rows (full 64/128-byte segments); the residual comes in the same way.  The per-column
+// bias is fetched with one coalesced load per chunk and broadcast through shared memory.
+template <int ESZ>
+__device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp, uint32_t lane, uint32_t tmem_base,
+                                             uint64_t* acc_full, uint64_t* acc_empty, uint8_t* stg_base) {
+    constexpr int CPR = ESZ * 2;        // 16-byte chunks per 32-column row: 4 (bf16) or 8 (fp32)
+    constexpr int EPC = 16 / ESZ;       // elements per 16-byte chunk
+    constexpr int RPI = 32 / CPR;       // rows covered by one warp-wide 16-byte access
+    const uint32_t ew = warp - 2u;
+    const uint32_t quad = warp & 3u;
+    const uint32_t grp = ew >> 2;
+    const uint32_t row = quad * 32u + lane;
+    const int32_t rw = static_cast<int32_t>(row) % p.bw;
+    const int32_t rh = (static_cast<int32_t>(row) / p.bw) % p.bh;
+    const int32_t rn = static_cast<int32_t>(row) / (p.bw * p.bh);
+    const bool has_bias = p.flags & EPI_BIAS, has_rb = p.flags & EPI_ROWBIAS, has_res = p.flags & EPI_RESIDUAL;
+    const bool vec = p.flags & EPI_VEC;
+    const int nchunks = (p.block_n + 31) >> 5;
+    const int c_begin = (p.mh == 2 || grp == 0) ? 0 : (nchunks + 1) >> 1;
+    const int c_end = p.mh == 2 ? nchunks : (grp == 0 ? (nchunks + 1) >> 1 : nchunks);
+    uint8_t* stg = stg_base + ew * 4096u;                                    // 32 rows x <= 128 B
+    float* sbias = reinterpret_cast<float*>(stg_base + 8 * 4096u) + ew * 32;  // 32 floats per warp
+    // swizzled byte offset of logical 16-byte chunk j of row r in a dense [32][n] chunk array
+    auto phys = [](int r, int j, int n) { return (r * n + (j ^ (((r * n) >> 3) & (n - 1)))) * 16; };
+    const int sr = lane / CPR, sj = lane % CPR;  // (row-in-group, chunk) this lane moves in the coalesced phases
+    uint32_t it = 0;
+    for (int32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        TileVars tv;
+        decompose_tile(p, tile, tv);
+        if (p.mh == 2 && grp == 1) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) tv.t[i] += (i == p.pair_var) ? 1 : 0;
+        }
+        const int32_t gw = tv.t[1] * p.bw + rw, gh = tv.t[2] * p.bh + rh, gn = tv.t[3] * p.bn + rn;
+        const bool row_ok = (rn < p.bn) && gw < p.W && gh < p.H && gn < p.N;
+        int64_t off = gw * p.ldw + gh * p.ldh + gn * p.ldn;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) off += tv.t[i] * p.otc[i];
+        // rows this lane moves in the coalesced phases (constant over the tile's chunks)
+        int64_t off_s[CPR];
+        uint32_t ok_s = 0;
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+            const int r = sr + RPI * i;
+            off_s[i] = __shfl_sync(0xffffffffu, off, r);
+            ok_s |= (__shfl_sync(0xffffffffu, row_ok ? 1u : 0u, r) & 1u) << i;
+        }
+        const int32_t col0 = tv.t[0] * p.block_n;
+        const uint32_t as = p.nacc == 2 ? (it & 1u) : 0u;
+        const uint32_t aphase = p.nacc == 2 ? ((it >> 1) & 1u) : (it & 1u);
+        mbar_wait(&acc_full[as], aphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + as * p.acc_stage_cols + (p.mh == 2 ? grp * p.acc_half_cols : 0u);
+        for (int ch = c_begin; ch < c_end; ++ch) {
+            const int32_t col = col0 + ch * 32;
+            const int32_t cvalid = min(32, min(p.block_n - ch * 32, p.ncols - col));  // valid columns of this chunk
+            __syncwarp();
+            uint32_t acc[32];
+            tmem_ld32(taddr + ch * 32, acc);            // issue the TMEM read first; global loads below overlap with it
+            float bval = 0.f;
+            if (has_bias && static_cast<int32_t>(lane) < cvalid) bval = __ldg(p.bias + col + lane);
+            if (vec && has_res && cvalid > 0) {         // residual: coalesced global -> staging (bf16, 4 chunks per row)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = (lane >> 2) + 8 * i, j = lane & 3;
+                    const int64_t off_r = __shfl_sync(0xffffffffu, off, r);
+                    const bool ok_r = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, r);
+                    uint4 q = make_uint4(0, 0, 0, 0);
+                    if (ok_r && j * 8 + 8 <= cvalid)
+                        q = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + off_r + col + j * 8));
+                    *reinterpret_cast<uint4*>(stg + phys(r, j, 4)) = q;
+                }
+            }
+            sbias[lane] = bval;
+            tmem_ld_wait();
+            __syncwarp();
+            if (cvalid <= 0) continue;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * p.alpha;
+            if (vec) {
+                if (has_bias) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = *reinterpret_cast<const float4*>(sbias + 4 * j);  // shared-memory broadcast
+                        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                    }
+                }
+                if (has_rb && row_ok) {
+                    const float4* b4 = reinterpret_cast<const float4*>(p.rowbias + (gn / p.rb_div) * p.rb_ld + col);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j * 4 + 4 <= cvalid) {
+                            const float4 b = __ldg(b4 + j);
+                            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                        }
+                    }
+                }
+                if (has_res) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 q = *reinterpret_cast<const uint4*>(stg + phys(lane, j, 4));
+                        v[8 * j + 0] += bf16_lo(q.x); v[8 * j + 1] += bf16_hi(q.x);
+                        v[8 * j + 2] += bf16_lo(q.y); v[8 * j + 3] += bf16_hi(q.y);
+                        v[8 * j + 4] += bf16_lo(q.z); v[8 * j + 5] += bf16_hi(q.z);
+                        v[8 * j + 6] += bf16_lo(q.w); v[8 * j + 7] += bf16_hi(q.w);
+                    }
+                    __syncwarp();
+                }
+                // own row -> staging
+                if (ESZ == 2) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 q;
+                        q.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+                        q.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+                        q.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+                        q.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+                        *reinterpret_cast<uint4*>(stg + phys(lane, j, 4)) = q;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(stg + phys(lane, j, 8)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                __syncwarp();
+                // staging -> global: 16 bytes per lane, whole row segments
+                const int nval = cvalid - sj * EPC;  // valid elements in this lane's chunk
+#pragma unroll
+                for (int i = 0; i < CPR; ++i) {
+                    if (!((ok_s >> i) & 1u) || nval <= 0) continue;
+                    const int r = sr + RPI * i;
+                    const uint4 q = *reinterpret_cast<const uint4*>(stg + phys(r, sj, CPR));
+                    const int64_t o = off_s[i] + col + sj * EPC;
+                    if (nval >= EPC) {
+                        if (ESZ == 2) {
+                            *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + o) = q;
+                        } else if (p.out_mode == OUT_F32) {
+                            *reinterpret_cast<uint4*>(static_cast<float*>(p.out) + o) = q;
+                        } else {
+                            red_add_f32x4(static_cast<float*>(p.out) + o, __uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z),
+                                          __uint_as_float(q.w));
+                        }
+                    } else {  // ragged last chunk: element-wise
+                        const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+                        for (int e = 0; e < nval; ++e) {
+                            if (ESZ == 2) {
+                                const uint32_t h = (w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
+                                reinterpret_cast<uint16_t*>(p.out)[o + e] = static_cast<uint16_t>(h);
+                            } else if (p.out_mode == OUT_F32) {
+                                static_cast<float*>(p.out)[o + e] = __uint_as_float(w4[e]);
+                            } else {
+                                atomicAdd(static_cast<float*>(p.out) + o + e, __uint_as_float(w4[e]));
+                            }
+                        }
+                    }
+                }
+            } else if (row_ok) {
+                // unaligned buffers: per-thread scalar path
+                for (int j = 0; j < cvalid; ++j) {
+                    float x = v[j];
+                    if (has_bias) x += p.bias[col + j];
+                    if (has_rb) x += p.rowbias[(gn / p.rb_div) * p.rb_ld + col + j];
+                    if (has_res) x += __bfloat162float(static_cast<const __nv_bfloat16*>(p.residual)[off + col + j]);
+                    if (ESZ == 2) static_cast<__nv_bfloat16*>(p.out)[off + col + j] = __float2bfloat16_rn(x);
+                    else if (p.out_mode == OUT_F32) static_cast<float*>(p.out)[off + col + j] = x;
+                    else atomicAdd(static_cast<float*>(p.out) + off + col + j, x);
+                }
+            }
+        }
+        tc_fence_before();
+        mbar_arrive(&acc_empty[as]);
+    }
+}
+
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -208,166 +386,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
         }
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..9)
-        // Two groups of four warps split the accumulator columns; within a group warp w owns TMEM lanes 32*(w%4)..+31,
-        // i.e. thread <-> output row.  Rows are strided in global memory, so every 32-column chunk goes through a
-        // per-warp swizzled staging tile: residual in / result out are moved with full 128-byte lines.
-        const uint32_t ew = warp - 2u;
-        const uint32_t quad = warp & 3u;
-        const uint32_t grp = ew >> 2;
-        const uint32_t row = quad * 32u + lane;
-        const int32_t rw = static_cast<int32_t>(row) % p.bw;
-        const int32_t rh = (static_cast<int32_t>(row) / p.bw) % p.bh;
-        const int32_t rn = static_cast<int32_t>(row) / (p.bw * p.bh);
-        const bool has_bias = p.flags & EPI_BIAS, has_rb = p.flags & EPI_ROWBIAS, has_res = p.flags & EPI_RESIDUAL;
-        const bool vec = p.flags & EPI_VEC;
-        const int nchunks = (p.block_n + 31) >> 5;
-        // mh == 1: the two warp groups split the columns of one 128-row accumulator;  mh == 2: group g drains row half g
-        const int c_begin = (p.mh == 2 || grp == 0) ? 0 : (nchunks + 1) >> 1;
-        const int c_end = p.mh == 2 ? nchunks : (grp == 0 ? (nchunks + 1) >> 1 : nchunks);
-        uint8_t* stg = reinterpret_cast<uint8_t*>(tmem_slot + 4) + ew * 4096u;  // 32 rows x <=128 B
-        const int esz = p.out_mode == OUT_BF16 ? 2 : 4;
-        const int cpr = esz * 2;  // 16-byte chunks per 32-column row: 4 (bf16) or 8 (fp32)
-        // swizzled position of logical chunk j of row r in a dense [32][cpr] chunk array
-        auto phys = [](int r, int j, int n) { return (r * n + (j ^ (((r * n) >> 3) & (n - 1)))) * 16; };
-        uint32_t it = 0;
-        for (int32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-            TileVars tv;
-            decompose_tile(p, tile, tv);
-            if (p.mh == 2 && grp == 1) {
-#pragma unroll
-                for (int i = 0; i < 6; ++i) tv.t[i] += (i == p.pair_var) ? 1 : 0;
-            }
-            const int32_t gw = tv.t[1] * p.bw + rw, gh = tv.t[2] * p.bh + rh, gn = tv.t[3] * p.bn + rn;
-            const bool row_ok = (rn < p.bn) && gw < p.W && gh < p.H && gn < p.N;
-            int64_t off = gw * p.ldw + gh * p.ldh + gn * p.ldn;
-#pragma unroll
-            for (int i = 0; i < 6; ++i) off += tv.t[i] * p.otc[i];
-            const int32_t col0 = tv.t[0] * p.block_n;
-            const uint32_t as = p.nacc == 2 ? (it & 1u) : 0u;
-            const uint32_t aphase = p.nacc == 2 ? ((it >> 1) & 1u) : (it & 1u);
-            mbar_wait(&acc_full[as], aphase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + as * p.acc_stage_cols + (p.mh == 2 ? grp * p.acc_half_cols : 0u);
-            for (int ch = c_begin; ch < c_end; ++ch) {
-                const int32_t col = col0 + ch * 32;
-                const int32_t cvalid = min(32, min(p.block_n - ch * 32, p.ncols - col));  // valid columns of this chunk
-                __syncwarp();
-                if (vec && has_res && cvalid > 0) {  // residual: coalesced global -> staging (bf16, 4 chunks per row)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = (lane >> 2) + 8 * i, j = lane & 3;
-                        const int64_t off_r = __shfl_sync(0xffffffffu, off, r);
-                        const bool ok_r = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, r);
-                        uint4 q = make_uint4(0, 0, 0, 0);
-                        if (ok_r && j * 8 + 8 <= cvalid)
-                            q = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + off_r + col + j * 8));
-                        *reinterpret_cast<uint4*>(stg + phys(r, j, 4)) = q;
-                    }
-                }
-                uint32_t acc[32];
-                tmem_ld32(taddr + ch * 32, acc);
-                tmem_ld_wait();
-                if (cvalid <= 0) continue;
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * p.alpha;
-                if (vec) {
-                    if (has_bias) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            if (j * 4 + 4 <= cvalid) {
-                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j);
-                                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-                            }
-                        }
-                    }
-                    if (has_rb && row_ok) {
-                        const float4* b4 = reinterpret_cast<const float4*>(p.rowbias + (gn / p.rb_div) * p.rb_ld + col);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            if (j * 4 + 4 <= cvalid) {
-                                const float4 b = __ldg(b4 + j);
-                                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-                            }
-                        }
-                    }
-                    if (has_res) {
-                        __syncwarp();
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint4 q = *reinterpret_cast<const uint4*>(stg + phys(lane, j, 4));
-                            v[8 * j + 0] += bf16_lo(q.x); v[8 * j + 1] += bf16_hi(q.x);
-                            v[8 * j + 2] += bf16_lo(q.y); v[8 * j + 3] += bf16_hi(q.y);
-                            v[8 * j + 4] += bf16_lo(q.z); v[8 * j + 5] += bf16_hi(q.z);
-                            v[8 * j + 6] += bf16_lo(q.w); v[8 * j + 7] += bf16_hi(q.w);
-                        }
-                        __syncwarp();
-                    }
-                    // own row -> staging
-                    if (esz == 2) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint4 q;
-                            q.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
-                            q.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-                            q.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-                            q.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-                            *reinterpret_cast<uint4*>(stg + phys(lane, j, 4)) = q;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            *reinterpret_cast<float4*>(stg + phys(lane, j, 8)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    }
-                    __syncwarp();
-                    // staging -> global, 16 bytes per lane, full lines per row
-                    const int epc = 16 / esz;  // elements per 16-byte chunk
-                    for (int i = 0; i < cpr; ++i) {
-                        const int r = lane / cpr + (32 / cpr) * i, j = lane % cpr;
-                        const int64_t off_r = __shfl_sync(0xffffffffu, off, r);
-                        const bool ok_r = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, r);
-                        const int nval = cvalid - j * epc;  // valid elements in this chunk
-                        if (!ok_r || nval <= 0) continue;
-                        const uint4 q = *reinterpret_cast<const uint4*>(stg + phys(r, j, cpr));
-                        if (nval >= epc) {
-                            if (p.out_mode == OUT_BF16) {
-                                *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + off_r + col + j * 8) = q;
-                            } else if (p.out_mode == OUT_F32) {
-                                *reinterpret_cast<uint4*>(static_cast<float*>(p.out) + off_r + col + j * 4) = q;
-                            } else {
-                                red_add_f32x4(static_cast<float*>(p.out) + off_r + col + j * 4, __uint_as_float(q.x), __uint_as_float(q.y),
-                                              __uint_as_float(q.z), __uint_as_float(q.w));
-                            }
-                        } else {  // ragged last chunk: element-wise
-                            const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
-                            for (int e = 0; e < nval; ++e) {
-                                if (p.out_mode == OUT_BF16) {
-                                    const uint32_t h = (w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
-                                    reinterpret_cast<uint16_t*>(p.out)[off_r + col + j * 8 + e] = static_cast<uint16_t>(h);
-                                } else if (p.out_mode == OUT_F32) {
-                                    static_cast<float*>(p.out)[off_r + col + j * 4 + e] = __uint_as_float(w4[e]);
-                                } else {
-                                    atomicAdd(static_cast<float*>(p.out) + off_r + col + j * 4 + e, __uint_as_float(w4[e]));
-                                }
-                            }
-                        }
-                    }
-                } else if (row_ok) {
-                    // unaligned buffers: per-thread scalar path
-                    for (int j = 0; j < cvalid; ++j) {
-                        float x = v[j];
-                        if (has_bias) x += p.bias[col + j];
-                        if (has_rb) x += p.rowbias[(gn / p.rb_div) * p.rb_ld + col + j];
-                        if (has_res) x += __bfloat162float(static_cast<const __nv_bfloat16*>(p.residual)[off + col + j]);
-                        if (p.out_mode == OUT_BF16) static_cast<__nv_bfloat16*>(p.out)[off + col + j] = __float2bfloat16_rn(x);
-                        else if (p.out_mode == OUT_F32) static_cast<float*>(p.out)[off + col + j] = x;
-                        else atomicAdd(static_cast<float*>(p.out) + off + col + j, x);
-                    }
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(&acc_empty[as]);
-        }
+        uint8_t* stg_base = reinterpret_cast<uint8_t*>(tmem_slot + 4);
+        if (p.out_mode == OUT_BF16) run_epilogue<2>(p, warp, lane, tmem_base, acc_full, acc_empty, stg_base);
+        else run_epilogue<4>(p, warp, lane, tmem_base, acc_full, acc_empty, stg_base);
     }
 
     tc_fence_before();

@@ -24,7 +24,7 @@ constexpr int kBlockM = 128;      // UMMA M (cta_group::1)
 constexpr int kBlockK = 64;       // bf16 elements per k-block (= one 128-byte swizzle row)
 constexpr int kMaxStages = 8;
 constexpr int kNumThreads = 320;  // warp0: TMA producer, warp1: MMA issuer, warps2-9: epilogue (two groups of four)
-constexpr int kEpilogueStagingBytes = 8 * 4096;  // one 32-row x 128-byte staging tile per epilogue warp
+constexpr int kEpilogueStagingBytes = 8 * 4096 + 8 * 128;  // per epilogue warp: a 32-row x 128-byte staging tile + 32 bias floats
 constexpr int kTmemCols = 512;    // two accumulator stages of up to 256 fp32 columns
 
 struct alignas(64) TmaOperand {

@@ -50,6 +50,7 @@ class DataParallelStep:
         self.passes = passes
         self.arena = ParamArena(unet) if adopt else None
         self.use_graph = use_graph
+        self.sync_gradients = True   # set False to run fwd+bwd only (profiling on a single rank)
         self._graph = None
 
     def _fwd_bwd(self, latents, noise, timesteps, text):
@@ -73,6 +74,6 @@ class DataParallelStep:
             loss = self._graph(*args)
         else:
             loss = self._fwd_bwd(*args)
-        if self.arena is not None:
+        if self.arena is not None and self.sync_gradients:
             allreduce_gradients(self.arena)
         return loss
