@@ -206,37 +206,24 @@ def main():
     torch.cuda.synchronize()
     launches_per_step = native.launch_count() - n0
 
-    # ---- dominant-kernel roofline: time every tensor-core (implicit-GEMM) launch of one eager step with CUDA events
+    # ---- dominant-kernel roofline: every tensor-core (implicit-GEMM) launch of the step, timed on the device.  One eager
+    # step records each launch's argument template; each distinct template is then replayed as a CUDA graph of
+    # back-to-back launches between CUDA events (eager per-launch events would count host launch gaps as kernel time).
     roof = None
-    if rank == 0:  # measured in eager mode BEFORE the graph is captured (graph-pool memory would distort eager allocation)
-        names = ["conv_fwd", "conv_dgrad", "conv_wgrad", "bgemm"]
-        saved = {n: getattr(prims, n) for n in names}
-        evs = []
-
-        def wrap(fn):
-            def inner(*a, **k):
-                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s.record()
-                r = fn(*a, **k)
-                e.record()
-                evs.append((s, e))
-                return r
-            return inner
-        for n in names:
-            setattr(prims, n, wrap(saved[n]))
-        try:
-            eager(*devin)
-            torch.cuda.synchronize()
-        finally:
-            for n in names:
-                setattr(prims, n, saved[n])
-        gemm_ms = sum(s.elapsed_time(e) for s, e in evs)
+    if rank == 0:  # before the step graph is captured (graph-pool memory would distort eager allocation)
+        from t2v_b200 import profiling
+        calls = profiling.record_calls(lambda: eager(*devin), ["conv_fwd", "conv_dgrad", "conv_wgrad", "bgemm"])
+        gemm_ms, n_gemm = 0.0, 0
+        for key, (cnt, _) in calls.items():
+            gemm_ms += profiling.replay_us(key, dev, reps=5) * cnt / 1e3
+            n_gemm += cnt
+        torch.cuda.empty_cache()
         peak_tf, peak_hbm, how = peaks()
         flops = (PASS_TFLOP_PER_CLIP if not args.small else float("nan")) * B
         ach = flops / (gemm_ms / 1e3) if gemm_ms > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM conv / linear / attention products)",
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
-                "launches": len(evs), "kernel_ms_per_step": gemm_ms, "share_of_step": None,
+                "launches": n_gemm, "distinct_shapes": len(calls), "kernel_ms_per_step": gemm_ms, "share_of_step": None,
                 "algorithmic_tflop_per_step": flops, "peak_source": how}
 
     def barrier():

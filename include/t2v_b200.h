@@ -165,12 +165,15 @@ int t2v_timestep_embedding(const int64_t* t, void* out, int32_t B, int32_t dim, 
 
 /* Self-attention over short sequences (L <= 32, head_dim 32 or 64) addressed by strides: the frame-axis attention of
  * TransformerTemporalModel (unet_3d_condition.py:147-152; unet_3d_blocks.py:331-340) without its permutes.
- * token t of sequence z, head h lives at  (z / inner) * outer_stride + (z % inner) * inner_stride + t * seq_stride + h * D. */
-int t2v_attn_small_fwd(const void* q, const void* k, const void* v, void* o, int64_t nseq, int32_t inner, int64_t outer_stride,
-                       int64_t inner_stride, int64_t seq_stride, int32_t heads, int32_t L, int32_t D, void* stream);
+ * Token t of sequence z lives in ROW (z / inner) * outer_rows + (z % inner) * inner_rows + t * seq_rows of a token matrix;
+ * q/k/v (and dq/dk/dv) have row pitch ld_in (so they may be column slices of one fused [rows][3C] QKV projection),
+ * o / dout have row pitch ld_out; head h occupies columns h*D .. h*D+D-1 of each pointer.                                 */
+int t2v_attn_small_fwd(const void* q, const void* k, const void* v, void* o, int64_t nseq, int32_t inner, int64_t outer_rows,
+                       int64_t inner_rows, int64_t seq_rows, int64_t ld_in, int64_t ld_out, int32_t heads, int32_t L, int32_t D,
+                       void* stream);
 int t2v_attn_small_bwd(const void* q, const void* k, const void* v, const void* dout, void* dq, void* dk, void* dv, int64_t nseq,
-                       int32_t inner, int64_t outer_stride, int64_t inner_stride, int64_t seq_stride, int32_t heads, int32_t L,
-                       int32_t D, void* stream);
+                       int32_t inner, int64_t outer_rows, int64_t inner_rows, int64_t seq_rows, int64_t ld_in, int64_t ld_out,
+                       int32_t heads, int32_t L, int32_t D, void* stream);
 
 #ifdef __cplusplus
 }

@@ -56,7 +56,8 @@ def conv_wgrad(x, dy, dw, stride=1, pads=(0, 0, 0, 0)):
 
 
 def _strided(t, sizes, strides):
-    return torch.as_strided(t.reshape(-1), sizes, strides)
+    """View of t's storage starting at t's first element (t may itself be a column slice of a wider matrix)."""
+    return torch.as_strided(t, sizes, strides, t.storage_offset())
 
 
 def bgemm(a, a_desc, b, b_desc, c, c_desc, M, N, K, Z1, Z2, alpha=1.0, out_mode=0):
@@ -271,31 +272,30 @@ def softmax_bwd(p, dp, n_valid, scale):
     return out
 
 
-def _seq_view(t, nseq, inner, outer_stride, inner_stride, seq_stride, heads, L, D):
-    return torch.as_strided(t.reshape(-1), (nseq // inner, inner, heads, L, D), (outer_stride, inner_stride, D, seq_stride, 1))
+def _seq_view(t, addr, out_side):
+    nseq, inner, outer_rows, inner_rows, seq_rows, ld_in, ld_out, heads, L, D = addr
+    ld = ld_out if out_side else ld_in
+    return torch.as_strided(t, (nseq // inner, inner, heads, L, D), (outer_rows * ld, inner_rows * ld, D, seq_rows * ld, 1),
+                            t.storage_offset())
 
 
-def attn_small_fwd(q, k, v, nseq, inner, outer_stride, inner_stride, seq_stride, heads, L, D):
-    args = (nseq, inner, outer_stride, inner_stride, seq_stride, heads, L, D)
-    Q, K, V = (_seq_view(t, *args).float() for t in (q, k, v))
+def attn_small_fwd(q, k, v, o, addr):
+    D = addr[-1]
+    Q, K, V = (_seq_view(t, addr, False).float() for t in (q, k, v))
     P = torch.softmax(Q @ K.transpose(-1, -2) * D ** -0.5, dim=-1)
-    o = torch.empty_like(q)
-    _seq_view(o, *args).copy_((P @ V).to(BF))
+    _seq_view(o, addr, True).copy_((P @ V).to(o.dtype))
     return o
 
 
 @torch.enable_grad()
-def attn_small_bwd(q, k, v, do, nseq, inner, outer_stride, inner_stride, seq_stride, heads, L, D):
-    args = (nseq, inner, outer_stride, inner_stride, seq_stride, heads, L, D)
-    Q, K, V = (_seq_view(t, *args).float().requires_grad_(True) for t in (q, k, v))
+def attn_small_bwd(q, k, v, do, dq, dk, dv, addr):
+    D = addr[-1]
+    Q, K, V = (_seq_view(t, addr, False).float().detach().requires_grad_(True) for t in (q, k, v))
     O = torch.softmax(Q @ K.transpose(-1, -2) * D ** -0.5, dim=-1) @ V
-    gq, gk, gv = torch.autograd.grad(O, (Q, K, V), _seq_view(do, *args).float())
-    outs = []
-    for g, like in ((gq, q), (gk, k), (gv, v)):
-        o = torch.empty_like(like)
-        _seq_view(o, *args).copy_(g.to(BF))
-        outs.append(o)
-    return tuple(outs)
+    gq, gk, gv = torch.autograd.grad(O, (Q, K, V), _seq_view(do, addr, True).float())
+    for g, dst in ((gq, dq), (gk, dk), (gv, dv)):
+        _seq_view(dst, addr, False).copy_(g.to(dst.dtype))
+    return dq, dk, dv
 
 
 def timestep_embedding(t, dim):

@@ -136,18 +136,62 @@ def test_softmax(rows, n, ld):
     close(prims.softmax_bwd(p_r, dp, n, 0.125), ref.softmax_bwd(p_r, dp, n, 0.125), 1e-2, "softmax bwd")
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("B,F,HW,heads,D", [(1, 16, 64, 5, 64), (2, 8, 16, 2, 64), (1, 24, 9, 1, 32), (1, 32, 4, 8, 64), (1, 1, 16, 2, 64)])
-def test_temporal_attention(B, F, HW, heads, D):
+def test_temporal_attention(B, F, HW, heads, D, fused):
+    """fused: q | k | v are column slices of one [rows, 3C] projection (row pitch 3C in, C out)."""
     prims, ref = _mods()
     g = _gen(7)
     C = heads * D
-    q, k, v, do = (rnd(g, B * F * HW, C) for _ in range(4))
-    addr = (B * HW, HW, F * HW * C, C, HW * C, heads, F, D)
-    close(prims.attn_small_fwd(q, k, v, *addr), ref.attn_small_fwd(q, k, v, *addr), 1e-2, "attn_small fwd")
-    got = prims.attn_small_bwd(q, k, v, do, *addr)
-    exp = ref.attn_small_bwd(q, k, v, do, *addr)
-    for name, a, b in zip("qkv", got, exp):
+    rows = B * F * HW
+    if fused:
+        qkv = rnd(g, rows, 3 * C)
+        q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    else:
+        q, k, v = (rnd(g, rows, C) for _ in range(3))
+    do = rnd(g, rows, C)
+    ld_in = 3 * C if fused else C
+    addr = (B * HW, HW, F * HW, 1, HW, ld_in, C, heads, F, D)
+    o, o_r = torch.zeros_like(do), torch.zeros_like(do)
+    close(prims.attn_small_fwd(q, k, v, o, addr), ref.attn_small_fwd(q, k, v, o_r, addr), 1e-2, "attn_small fwd")
+    # gradients land in the layout of the inputs (the fused [rows, 3C] buffer when fused)
+    got, exp = torch.zeros(rows, 3 * C, device=DEV, dtype=do.dtype), torch.zeros(rows, 3 * C, device=DEV, dtype=do.dtype)
+    if fused:
+        gaddr = addr
+        sl = lambda t: (t[:, :C], t[:, C:2 * C], t[:, 2 * C:])
+    else:
+        gaddr = addr
+        sl = lambda t: tuple(t.view(3, rows, C)[i] for i in range(3))
+    prims.attn_small_bwd(q, k, v, do, *sl(got), gaddr)
+    ref.attn_small_bwd(q, k, v, do, *sl(exp), gaddr)
+    for name, a, b in zip("qkv", sl(got), sl(exp)):
         close(a, b, 1.5e-2, f"attn_small d{name}")
+
+
+@pytest.mark.parametrize("cross", [False, True])
+def test_fused_projection_attention_matches_unfused(cross):
+    """ops.attention_fused on [.., 3C] / [.., 2C] projections == ops.attention on separate q, k, v (values and gradients)."""
+    from t2v_b200 import ops
+    g = _gen(21)
+    Nb, Lq, Lk, heads, D = (2, 2304, 77, 5, 64) if cross else (3, 256, 256, 5, 64)
+    C = heads * D
+    q, k, v = rnd(g, Nb, Lq, C), rnd(g, Nb, Lk, C), rnd(g, Nb, Lk, C)
+    do = rnd(g, Nb, Lq, C)
+    qs, ks, vs = (t.clone().requires_grad_(True) for t in (q, k, v))
+    ops.attention(qs, ks, vs, heads).backward(do)
+    if cross:
+        a, b = q.clone().requires_grad_(True), torch.cat([k, v], -1).requires_grad_(True)
+        out = ops.attention_fused(a, b, heads)
+        out.backward(do)
+        gq, gk, gv = a.grad, b.grad[..., :C], b.grad[..., C:]
+    else:
+        a = torch.cat([q, k, v], -1).requires_grad_(True)
+        out = ops.attention_fused(a, None, heads)
+        out.backward(do)
+        gq, gk, gv = a.grad[..., :C], a.grad[..., C:2 * C], a.grad[..., 2 * C:]
+    close(out, ops.attention(q, k, v, heads), 1e-2, "fused attention fwd")
+    for name, x, y in (("q", gq, qs.grad), ("k", gk, ks.grad), ("v", gv, vs.grad)):
+        close(x, y, 1.5e-2, f"fused attention d{name}")
 
 
 def test_latent_boundary_and_loss():

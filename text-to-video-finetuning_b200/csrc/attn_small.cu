@@ -18,13 +18,16 @@ namespace t2v {
 constexpr int kWarpsPerBlock = 4;
 constexpr int kMaxL = 32;
 
+// Sequence addressing in ROWS of a token matrix; q/k/v (and their gradients) have row pitch ld_in - which lets them be
+// column slices of one fused [rows][3C] QKV projection - while o / dO have row pitch ld_out.
 struct SeqAddr {
-    int64_t outer_stride, inner_stride, seq_stride;
+    int64_t outer_rows, inner_rows, seq_rows;
+    int64_t ld_in, ld_out;
     int32_t inner;
 };
 
-__device__ __forceinline__ int64_t seq_base(const SeqAddr& a, int64_t z, int h, int D) {
-    return (z / a.inner) * a.outer_stride + (z % a.inner) * a.inner_stride + int64_t(h) * D;
+__device__ __forceinline__ int64_t seq_row(const SeqAddr& a, int64_t z) {
+    return (z / a.inner) * a.outer_rows + (z % a.inner) * a.inner_rows;
 }
 
 template <int D>
@@ -58,11 +61,13 @@ __global__ void attn_small_fwd_kernel(const __nv_bfloat16* __restrict__ q, const
     for (int64_t w = blockIdx.x * int64_t(nwarps) + warp; w < total; w += int64_t(gridDim.x) * nwarps) {
         const int64_t z = w / heads;
         const int h = int(w % heads);
-        const int64_t base = seq_base(a, z, h, D);
+        const int64_t row0 = seq_row(a, z);
+        const int64_t base = row0 * a.ld_in + int64_t(h) * D, sstr = a.seq_rows * a.ld_in;
+        const int64_t obase = row0 * a.ld_out + int64_t(h) * D, ostr = a.seq_rows * a.ld_out;
         __syncwarp();
-        load_tile<D>(q, base, a.seq_stride, L, sq, lane);
-        load_tile<D>(k, base, a.seq_stride, L, sk, lane);
-        load_tile<D>(v, base, a.seq_stride, L, sv, lane);
+        load_tile<D>(q, base, sstr, L, sq, lane);
+        load_tile<D>(k, base, sstr, L, sk, lane);
+        load_tile<D>(v, base, sstr, L, sv, lane);
         __syncwarp();
         for (int i = 0; i < L; ++i) {
             float s = -INFINITY;
@@ -87,11 +92,11 @@ __global__ void attn_small_fwd_kernel(const __nv_bfloat16* __restrict__ q, const
                     a0 += pj * sv[j * (D + 1) + 2 * lane];
                     a1 += pj * sv[j * (D + 1) + 2 * lane + 1];
                 }
-                reinterpret_cast<__nv_bfloat162*>(o + base + i * a.seq_stride)[lane] = __floats2bfloat162_rn(a0, a1);
+                reinterpret_cast<__nv_bfloat162*>(o + obase + i * ostr)[lane] = __floats2bfloat162_rn(a0, a1);
             } else {
                 float a0 = 0.f;
                 for (int j = 0; j < L; ++j) a0 += __shfl_sync(0xffffffffu, p, j) * sv[j * (D + 1) + lane];
-                o[base + i * a.seq_stride + lane] = __float2bfloat16_rn(a0);
+                o[obase + i * ostr + lane] = __float2bfloat16_rn(a0);
             }
         }
     }
@@ -118,12 +123,14 @@ __global__ void attn_small_bwd_kernel(const __nv_bfloat16* __restrict__ q, const
     for (int64_t w = blockIdx.x * int64_t(nwarps) + warp; w < total; w += int64_t(gridDim.x) * nwarps) {
         const int64_t z = w / heads;
         const int h = int(w % heads);
-        const int64_t base = seq_base(a, z, h, D);
+        const int64_t row0 = seq_row(a, z);
+        const int64_t base = row0 * a.ld_in + int64_t(h) * D, sstr = a.seq_rows * a.ld_in;
+        const int64_t obase = row0 * a.ld_out + int64_t(h) * D, ostr = a.seq_rows * a.ld_out;
         __syncwarp();
-        load_tile<D>(q, base, a.seq_stride, L, sq, lane);
-        load_tile<D>(k, base, a.seq_stride, L, sk, lane);
-        load_tile<D>(v, base, a.seq_stride, L, sv, lane);
-        load_tile<D>(dout, base, a.seq_stride, L, sd, lane);
+        load_tile<D>(q, base, sstr, L, sq, lane);
+        load_tile<D>(k, base, sstr, L, sk, lane);
+        load_tile<D>(v, base, sstr, L, sv, lane);
+        load_tile<D>(dout, obase, ostr, L, sd, lane);
         __syncwarp();
         for (int i = 0; i < L; ++i) {
             float s = -INFINITY, dp = 0.f;
@@ -191,7 +198,7 @@ __global__ void attn_small_bwd_kernel(const __nv_bfloat16* __restrict__ q, const
             for (int ii = 0; ii < SLAB; ++ii) {
                 const int i = i0 + ii;
                 if (i >= L) break;
-                const int64_t off = base + i * a.seq_stride;
+                const int64_t off = base + i * sstr;
                 if (D == 64) {
                     reinterpret_cast<__nv_bfloat162*>(dq + off)[lane] = __floats2bfloat162_rn(aq[ii][0], aq[ii][NP - 1]);
                     reinterpret_cast<__nv_bfloat162*>(dk + off)[lane] = __floats2bfloat162_rn(ak[ii][0], ak[ii][NP - 1]);
@@ -220,8 +227,9 @@ static int attn_small_config(int L, int D, int tiles, int extra_floats, int& war
 
 extern "C" {
 
-int t2v_attn_small_fwd(const void* q, const void* k, const void* v, void* o, int64_t nseq, int32_t inner, int64_t outer_stride,
-                       int64_t inner_stride, int64_t seq_stride, int32_t heads, int32_t L, int32_t D, void* stream) {
+int t2v_attn_small_fwd(const void* q, const void* k, const void* v, void* o, int64_t nseq, int32_t inner, int64_t outer_rows,
+                       int64_t inner_rows, int64_t seq_rows, int64_t ld_in, int64_t ld_out, int32_t heads, int32_t L, int32_t D,
+                       void* stream) {
     if (L < 1 || L > kMaxL) return fail(-2, "attn_small: L=%d out of range (1..%d)", L, kMaxL);
     if (D != 64 && D != 32) return fail(-2, "attn_small: head_dim %d unsupported (32 or 64)", D);
     static bool attr_done = false;
@@ -230,7 +238,8 @@ int t2v_attn_small_fwd(const void* q, const void* k, const void* v, void* o, int
         cudaFuncSetAttribute(attn_small_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
         attr_done = true;
     }
-    SeqAddr a{outer_stride, inner_stride, seq_stride, inner};
+    if (ld_in % 8 || ld_out % 8) return fail(-2, "attn_small: row pitches must be multiples of 8 elements");
+    SeqAddr a{outer_rows, inner_rows, seq_rows, ld_in, ld_out, inner};
     int warps;
     size_t smem;
     attn_small_config(L, D, 3, 0, warps, smem);
@@ -248,8 +257,8 @@ int t2v_attn_small_fwd(const void* q, const void* k, const void* v, void* o, int
 }
 
 int t2v_attn_small_bwd(const void* q, const void* k, const void* v, const void* dout, void* dq, void* dk, void* dv, int64_t nseq,
-                       int32_t inner, int64_t outer_stride, int64_t inner_stride, int64_t seq_stride, int32_t heads, int32_t L,
-                       int32_t D, void* stream) {
+                       int32_t inner, int64_t outer_rows, int64_t inner_rows, int64_t seq_rows, int64_t ld_in, int64_t ld_out,
+                       int32_t heads, int32_t L, int32_t D, void* stream) {
     if (L < 1 || L > kMaxL) return fail(-2, "attn_small: L=%d out of range (1..%d)", L, kMaxL);
     if (D != 64 && D != 32) return fail(-2, "attn_small: head_dim %d unsupported (32 or 64)", D);
     static bool attr_done = false;
@@ -258,7 +267,8 @@ int t2v_attn_small_bwd(const void* q, const void* k, const void* v, const void* 
         cudaFuncSetAttribute(attn_small_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
         attr_done = true;
     }
-    SeqAddr a{outer_stride, inner_stride, seq_stride, inner};
+    if (ld_in % 8 || ld_out % 8) return fail(-2, "attn_small: row pitches must be multiples of 8 elements");
+    SeqAddr a{outer_rows, inner_rows, seq_rows, ld_in, ld_out, inner};
     int warps;
     size_t smem;
     attn_small_config(L, D, 4, 2 * L * L, warps, smem);

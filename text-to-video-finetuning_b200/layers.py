@@ -260,11 +260,28 @@ class BasicTransformerBlock(nn.Module):
         self.norm3 = nn.LayerNorm(dim)
         self.ff = FeedForward(dim, dropout=dropout, activation_fn=activation_fn)
 
+    @staticmethod
+    def _fused(attn):
+        """('qkv' | 'kv', FusedWeight) when the runtime arena laid this attention's projections out back to back and
+        none of them is wrapped (LoRA) - then they run as one GEMM."""
+        f = getattr(attn, "_t2v_fused", None)
+        if f is None or not f[1].usable():
+            return None
+        if not all(type(m) is nn.Linear for m in (attn.to_q, attn.to_k, attn.to_v)):
+            return None
+        return f
+
     def forward(self, x, context, attend, attend_cross=None):
         for attn, norm in ((self.attn1, self.norm1), (self.attn2, self.norm2)):
             res, h = ops.fork(x)
             n = run_layer_norm(norm, h)
-            if attn.is_cross:
+            fused = self._fused(attn)
+            if fused is not None and fused[0] == "qkv" and not attn.is_cross:
+                a = attend(ops.linear(n, fused[1]), None, None, attn)
+            elif fused is not None and fused[0] == "kv" and attn.is_cross:
+                q = run_linear(attn.to_q, n)
+                a = attend_cross(q, ops.linear(context, fused[1]), None, attn)
+            elif attn.is_cross:
                 q = run_linear(attn.to_q, n)
                 c1, c2 = ops.fork(context)
                 k, v = run_linear(attn.to_k, c1), run_linear(attn.to_v, c2)
@@ -304,12 +321,16 @@ class Transformer2DModel(nn.Module):
         h = run_group_norm(self.norm, h, False, N).view(N * H * W, C)
         h = run_linear(self.proj_in, h)
 
-        def attend(q, k, v, attn):  # per-frame spatial self-attention
+        def attend(q, k, v, attn):  # per-frame spatial self-attention (k is None: q is the fused [rows, 3C] projection)
             L = H * W
+            if k is None:
+                return ops.attention_fused(q.view(N, L, -1), None, attn.heads).view(N * L, -1)
             return ops.attention(q.view(N, L, -1), k.view(N, L, -1), v.view(N, L, -1), attn.heads).view(N * L, -1)
 
         def attend_cross(q, k, v, attn):  # all frames of a clip attend to that clip's text tokens: K/V once per clip
             Lq = num_frames * H * W
+            if v is None:                 # k is the fused [B*Lctx, 2C] projection of the text tokens
+                return ops.attention_fused(q.view(B, Lq, -1), k.view(B, -1, k.shape[-1]), attn.heads).view(B * Lq, -1)
             return ops.attention(q.view(B, Lq, -1), k.view(B, -1, k.shape[-1]), v.view(B, -1, v.shape[-1]),
                                  attn.heads).view(B * Lq, -1)
 
@@ -345,6 +366,8 @@ class TransformerTemporalModel(nn.Module):
         h = run_linear(self.proj_in, h)
 
         def attend(q, k, v, attn):
+            if k is None:
+                return ops.temporal_attention_fused(q, attn.heads, B, num_frames, H * W)
             return ops.temporal_attention(q, k, v, attn.heads, B, num_frames, H * W)
 
         h = self.transformer_blocks[0](h, None, attend)

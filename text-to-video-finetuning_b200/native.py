@@ -108,8 +108,8 @@ def _declare(lib):
     lib.t2v_softmax_fwd.argtypes = [vp, vp, i64, i32, i32, i32, vp]
     lib.t2v_softmax_bwd.argtypes = [vp, vp, vp, i64, i32, i32, i32, f32, vp]
     lib.t2v_timestep_embedding.argtypes = [vp, vp, i32, i32, vp]
-    lib.t2v_attn_small_fwd.argtypes = [vp] * 4 + [i64, i32, i64, i64, i64, i32, i32, i32, vp]
-    lib.t2v_attn_small_bwd.argtypes = [vp] * 7 + [i64, i32, i64, i64, i64, i32, i32, i32, vp]
+    lib.t2v_attn_small_fwd.argtypes = [vp] * 4 + [i64, i32, i64, i64, i64, i64, i64, i32, i32, i32, vp]
+    lib.t2v_attn_small_bwd.argtypes = [vp] * 7 + [i64, i32, i64, i64, i64, i64, i64, i32, i32, i32, vp]
     for name in EXPORTS:
         getattr(lib, name)  # every declared symbol must be exported
     return lib

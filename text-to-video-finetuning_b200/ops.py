@@ -30,9 +30,27 @@ def _phys(p):
     return v
 
 
+class FusedWeight:
+    """Several linear weights that sit back to back in the ParamArena (to_q|to_k|to_v of one Attention, or to_k|to_v for
+    cross-attention) viewed as ONE [sum(out), 1, 1, in] matrix: one GEMM instead of three in forward, dgrad and wgrad."""
+
+    def __init__(self, params, shadow, grad):
+        self.params, self.shadow, self.grad = params, shadow, grad
+
+    @property
+    def requires_grad(self):
+        return all(p.requires_grad for p in self.params)
+
+    def usable(self):
+        flags = {p.requires_grad for p in self.params}
+        return len(flags) == 1   # all trainable or all frozen
+
+
 def weight_bf16(p):
     """bf16 compute copy of a weight in kernel layout.  Uses the per-step flat shadow when the model has been
     prepared by runtime.ParamArena, otherwise casts on the fly (our cast kernel)."""
+    if isinstance(p, FusedWeight):
+        return p.shadow
     sh = getattr(p, "_t2v_shadow", None)
     if sh is not None:
         return sh
@@ -46,6 +64,8 @@ def weight_bf16(p):
 
 def grad_phys(p):
     """fp32 accumulation buffer for a weight, in kernel layout (allocates param.grad on first use)."""
+    if isinstance(p, FusedWeight):
+        return p.grad
     if p.grad is None:
         p.grad = torch.zeros_like(p, memory_format=torch.preserve_format)
     g = _phys(p.grad)
@@ -110,7 +130,9 @@ class _Conv(Function):
     """y = conv(x, W) + bias + rowbias[n // rb_div] + residual on the tcgen05 implicit-GEMM kernel."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, rowbias, residual, stride, pads, rb_div, out_fp32, cin_pad, cout_pad, alpha):
+    def forward(ctx, x, weight, bias, rowbias, residual, stride, pads, rb_div, out_fp32, cin_pad, cout_pad, alpha, anchor=None):
+        # `anchor`: a trainable tensor standing in for a FusedWeight (not a tensor) so that autograd still schedules
+        # this node when x itself needs no gradient (cross-attention K|V projection of the text states)
         w = weight_bf16(weight)
         cin_pad = x.shape[-1] - w.shape[-1]        # boundary tensors arrive zero-padded to 8 channels
         cout_pad = (-w.shape[0]) % 8                # ... and leave padded to a multiple of 8
@@ -169,7 +191,7 @@ class _Conv(Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = prims.conv_dgrad(dy, w, (x.shape[1], x.shape[2]), stride, pads)
-        return dx, None, None, d_rowbias, d_res, None, None, None, None, None, None, None
+        return dx, None, None, d_rowbias, d_res, None, None, None, None, None, None, None, None
 
 
 def conv(x, weight, bias=None, rowbias=None, residual=None, stride=1, pads=(1, 1, 1, 1), rb_div=1, out_fp32=False,
@@ -181,7 +203,8 @@ def linear(x, weight, bias=None, residual=None, out_fp32=False, alpha=1.0):
     """x [rows, in] -> [rows, out] through the same kernel (a 1x1 convolution over a rows x 1 image)."""
     rows, cin = x.shape
     res4 = residual.view(1, 1, rows, -1) if residual is not None else None
-    y = _Conv.apply(x.view(1, 1, rows, cin), weight, bias, None, res4, 1, (0, 0, 0, 0), 1, out_fp32, 0, 0, float(alpha))
+    anchor = weight.params[0] if isinstance(weight, FusedWeight) and weight.requires_grad else None
+    y = _Conv.apply(x.view(1, 1, rows, cin), weight, bias, None, res4, 1, (0, 0, 0, 0), 1, out_fp32, 0, 0, float(alpha), anchor)
     return y.view(rows, -1)
 
 
@@ -336,23 +359,64 @@ def _rup8(n):
     return (n + 7) // 8 * 8
 
 
+def _attn_core_fwd(q, k, v, heads):
+    """q [Nb, Lq, C], k/v [Nb, Lk, C]: row-contiguous views (arbitrary row pitch).  Returns (o contiguous, p)."""
+    Nb, Lq, C = q.shape
+    Lk = k.shape[1]
+    D = C // heads
+    ld = _rup8(Lk)
+    scale = D ** -0.5
+    s = torch.empty((Nb, heads, Lq, ld), device=q.device, dtype=torch.float32)
+    prims.bgemm(q, (1, q.stride(1), q.stride(0), D), k, (1, k.stride(1), k.stride(0), D), s, (ld, heads * Lq * ld, Lq * ld),
+                Lq, Lk, D, Nb, heads, scale, 1)
+    p = prims.softmax_fwd(s, Lk, ld)
+    del s
+    o = torch.empty((Nb, Lq, C), device=q.device, dtype=q.dtype)
+    prims.bgemm(p, (1, ld, heads * Lq * ld, Lq * ld), v, (0, v.stride(1), v.stride(0), D), o, (C, Lq * C, D), Lq, D, Lk, Nb, heads, 1.0, 0)
+    return o, p
+
+
+def _attn_core_bwd(q, k, v, p, do, dq, dk, dv, heads):
+    """Gradients of _attn_core_fwd written into the (row-contiguous, possibly column-sliced) views dq / dk / dv."""
+    Nb, Lq, C = q.shape
+    Lk = k.shape[1]
+    D = C // heads
+    ld = p.shape[-1]
+    scale = D ** -0.5
+    pd = (ld, heads * Lq * ld, Lq * ld)
+    dod = (do.stride(1), do.stride(0), D)
+    # dV = P^T dO and dK = dS^T Q contract over Lq.  For cross-attention (Lq = F*H*W >> Lk = 77) there are only
+    # Nb*heads output tiles, so those two run split-K into an fp32 buffer (red.add) followed by one cast.
+    split = Lq >= 2048 and Lk <= 256
+
+    def over_lq(a_mat, b_mat, out):
+        bd = (0, b_mat.stride(1), b_mat.stride(0), D)
+        if not split:
+            prims.bgemm(a_mat, (0,) + pd, b_mat, bd, out, (out.stride(1), out.stride(0), D), Lk, D, Lq, Nb, heads, 1.0, 0)
+            return
+        acc = torch.zeros((Nb, Lk, C), device=out.device, dtype=torch.float32)
+        prims.bgemm(a_mat, (0,) + pd, b_mat, bd, acc, (C, Lk * C, D), Lk, D, Lq, Nb, heads, 1.0, 2)
+        if out.is_contiguous():
+            prims.cast_f32_bf16(acc, out)
+        else:
+            out.copy_(prims.cast_f32_bf16(acc))
+
+    over_lq(p, do, dv)
+    dp = torch.empty((Nb, heads, Lq, ld), device=q.device, dtype=torch.float32)  # dP = dO V^T
+    prims.bgemm(do, (1,) + dod, v, (1, v.stride(1), v.stride(0), D), dp, pd, Lq, Lk, D, Nb, heads, 1.0, 1)
+    ds = prims.softmax_bwd(p, dp, Lk, scale)
+    del dp
+    prims.bgemm(ds, (1,) + pd, k, (0, k.stride(1), k.stride(0), D), dq, (dq.stride(1), dq.stride(0), D), Lq, D, Lk, Nb, heads, 1.0, 0)  # dQ = dS K
+    over_lq(ds, q, dk)                                                                                                                   # dK = dS^T Q
+
+
 class _Attention(Function):
     """softmax(q k^T / sqrt(d)) v for token matrices q [Nb, Lq, H*D], k/v [Nb, Lk, H*D]; the four contractions run
     as batched GEMMs on the tcgen05 kernel, the row softmax in between as one HBM-bound pass."""
 
     @staticmethod
     def forward(ctx, q, k, v, heads):
-        Nb, Lq, C = q.shape
-        Lk = k.shape[1]
-        D = C // heads
-        ld = _rup8(Lk)
-        scale = D ** -0.5
-        s = torch.empty((Nb, heads, Lq, ld), device=q.device, dtype=torch.float32)
-        prims.bgemm(q, (1, C, Lq * C, D), k, (1, C, Lk * C, D), s, (ld, heads * Lq * ld, Lq * ld), Lq, Lk, D, Nb, heads, scale, 1)
-        p = prims.softmax_fwd(s, Lk, ld)
-        del s
-        o = torch.empty_like(q)
-        prims.bgemm(p, (1, ld, heads * Lq * ld, Lq * ld), v, (0, C, Lk * C, D), o, (C, Lq * C, D), Lq, D, Lk, Nb, heads, 1.0, 0)
+        o, p = _attn_core_fwd(q, k, v, heads)
         ctx.save_for_backward(q, k, v, p)
         ctx.heads = heads
         return o
@@ -360,35 +424,8 @@ class _Attention(Function):
     @staticmethod
     def backward(ctx, do):
         q, k, v, p = ctx.saved_tensors
-        heads = ctx.heads
-        do = _cont(do)
-        Nb, Lq, C = q.shape
-        Lk = k.shape[1]
-        D = C // heads
-        ld = p.shape[-1]
-        scale = D ** -0.5
-        pd = (ld, heads * Lq * ld, Lq * ld)
-        # dV = P^T dO and dK = dS^T Q contract over Lq.  For cross-attention (Lq = F*H*W >> Lk = 77) there are only
-        # Nb*heads output tiles, so those two run split-K into an fp32 buffer (red.add) followed by one cast.
-        split = Lq >= 2048 and Lk <= 256
-
-        def over_lq(a_mat, b_mat, like):
-            if not split:
-                out = torch.empty_like(like)
-                prims.bgemm(a_mat, (0,) + pd, b_mat, (0, C, Lq * C, D), out, (C, Lk * C, D), Lk, D, Lq, Nb, heads, 1.0, 0)
-                return out
-            acc = torch.zeros(like.shape, device=like.device, dtype=torch.float32)
-            prims.bgemm(a_mat, (0,) + pd, b_mat, (0, C, Lq * C, D), acc, (C, Lk * C, D), Lk, D, Lq, Nb, heads, 1.0, 2)
-            return prims.cast_f32_bf16(acc)
-
-        dv = over_lq(p, do, v)
-        dp = torch.empty((Nb, heads, Lq, ld), device=q.device, dtype=torch.float32)  # dP = dO V^T
-        prims.bgemm(do, (1, C, Lq * C, D), v, (1, C, Lk * C, D), dp, pd, Lq, Lk, D, Nb, heads, 1.0, 1)
-        ds = prims.softmax_bwd(p, dp, Lk, scale)
-        del dp
-        dq = torch.empty_like(q)  # dQ = dS K
-        prims.bgemm(ds, (1,) + pd, k, (0, C, Lk * C, D), dq, (C, Lq * C, D), Lq, D, Lk, Nb, heads, 1.0, 0)
-        dk = over_lq(ds, q, k)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        _attn_core_bwd(q, k, v, p, _cont(do), dq, dk, dv, ctx.heads)
         return dq, dk, dv, None
 
 
@@ -396,27 +433,90 @@ def attention(q, k, v, heads):
     return _Attention.apply(q, k, v, heads)
 
 
-class _TemporalAttention(Function):
-    """Self-attention along the frame axis on frames-major tokens [B*F*HW, H*D] (no permute; see attn_small.cu)."""
+class _AttentionFused(Function):
+    """Same attention on fused projections: self-attention takes qkv [Nb, L, 3C] (kv None), cross-attention takes
+    q [Nb, Lq, C] and kv [Nb, Lk, 2C].  q / k / v are column slices of those buffers (no copies), and the gradient is
+    produced directly in the fused layout, so autograd never sees the slicing."""
 
     @staticmethod
-    def forward(ctx, q, k, v, heads, B, F, HW):
-        C = q.shape[-1]
-        D = C // heads
-        addr = (B * HW, HW, F * HW * C, C, HW * C, heads, F, D)
-        ctx.addr = addr
+    def forward(ctx, qkv, kv, heads):
+        if kv is None:
+            C = qkv.shape[-1] // 3
+            q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        else:
+            C = qkv.shape[-1]
+            q, k, v = qkv, kv[..., :C], kv[..., C:]
+        o, p = _attn_core_fwd(q, k, v, heads)
+        ctx.save_for_backward(qkv, kv, p)
+        ctx.heads = heads
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        qkv, kv, p = ctx.saved_tensors
+        dqkv = torch.empty_like(qkv)
+        if kv is None:
+            C = qkv.shape[-1] // 3
+            q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+            dq, dk, dv = dqkv[..., :C], dqkv[..., C:2 * C], dqkv[..., 2 * C:]
+            dkv = None
+        else:
+            C = qkv.shape[-1]
+            dkv = torch.empty_like(kv)
+            q, k, v = qkv, kv[..., :C], kv[..., C:]
+            dq, dk, dv = dqkv, dkv[..., :C], dkv[..., C:]
+        _attn_core_bwd(q, k, v, p, _cont(do), dq, dk, dv, ctx.heads)
+        return dqkv, dkv, None
+
+
+def attention_fused(qkv, kv, heads):
+    return _AttentionFused.apply(qkv, kv, heads)
+
+
+def _temporal_addr(B, F, HW, heads, D, ld_in, ld_out):
+    # frames-major tokens: row of (b, f, hw) = (b*F + f)*HW + hw; a sequence runs over f with b, hw fixed
+    return (B * HW, HW, F * HW, 1, HW, ld_in, ld_out, heads, F, D)
+
+
+class _TemporalAttention(Function):
+    """Self-attention along the frame axis on frames-major tokens [B*F*HW, H*D] (no permute; see attn_small.cu).
+    `fused`: q is the [rows, 3C] QKV projection and k, v are None."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, heads, B, F, HW, fused):
+        if fused:
+            C = q.shape[-1] // 3
+            qq, kk, vv = q[:, :C], q[:, C:2 * C], q[:, 2 * C:]
+        else:
+            C = q.shape[-1]
+            qq, kk, vv = q, k, v
+        addr = _temporal_addr(B, F, HW, heads, C // heads, q.shape[-1], C)
+        o = torch.empty((q.shape[0], C), device=q.device, dtype=q.dtype)
+        prims.attn_small_fwd(qq, kk, vv, o, addr)
+        ctx.addr, ctx.fused = addr, fused
         ctx.save_for_backward(q, k, v)
-        return prims.attn_small_fwd(q, k, v, *addr)
+        return o
 
     @staticmethod
     def backward(ctx, do):
         q, k, v = ctx.saved_tensors
-        dq, dk, dv = prims.attn_small_bwd(q, k, v, _cont(do), *ctx.addr)
-        return dq, dk, dv, None, None, None, None
+        do = _cont(do)
+        if ctx.fused:
+            C = q.shape[-1] // 3
+            dqkv = torch.empty_like(q)
+            prims.attn_small_bwd(q[:, :C], q[:, C:2 * C], q[:, 2 * C:], do, dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], ctx.addr)
+            return dqkv, None, None, None, None, None, None, None
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        prims.attn_small_bwd(q, k, v, do, dq, dk, dv, ctx.addr)
+        return dq, dk, dv, None, None, None, None, None
 
 
 def temporal_attention(q, k, v, heads, B, F, HW):
-    return _TemporalAttention.apply(q, k, v, heads, B, F, HW)
+    return _TemporalAttention.apply(q, k, v, heads, B, F, HW, False)
+
+
+def temporal_attention_fused(qkv, heads, B, F, HW):
+    return _TemporalAttention.apply(qkv, None, None, heads, B, F, HW, True)
 
 
 # ---------------------------------------------------------------------------------------------------- latent boundary

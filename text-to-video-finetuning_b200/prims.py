@@ -291,19 +291,22 @@ def softmax_bwd(p, dp, n_valid, scale):
     return ds
 
 
-def attn_small_fwd(q, k, v, nseq, inner, outer_stride, inner_stride, seq_stride, heads, L, D):
-    _chk_bf16(q, k, v)
-    o = torch.empty_like(q)
-    native.check(native.lib().t2v_attn_small_fwd(_p(q), _p(k), _p(v), _p(o), nseq, inner, outer_stride, inner_stride, seq_stride,
-                                                 heads, L, D, _stream()))
+def _chk_rows_bf16(*ts):
+    """bf16 CUDA matrices whose rows are contiguous (column slices of a wider matrix are fine)."""
+    for t in ts:
+        assert t.dtype == torch.bfloat16 and t.is_cuda and t.stride(-1) == 1, (t.dtype, t.shape, t.stride())
+
+
+def attn_small_fwd(q, k, v, o, addr):
+    """addr = (nseq, inner, outer_rows, inner_rows, seq_rows, ld_in, ld_out, heads, L, D); q/k/v may be column slices."""
+    _chk_rows_bf16(q, k, v, o)
+    native.check(native.lib().t2v_attn_small_fwd(_p(q), _p(k), _p(v), _p(o), *addr, _stream()))
     return o
 
 
-def attn_small_bwd(q, k, v, do, nseq, inner, outer_stride, inner_stride, seq_stride, heads, L, D):
-    _chk_bf16(q, k, v, do)
-    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-    native.check(native.lib().t2v_attn_small_bwd(_p(q), _p(k), _p(v), _p(do), _p(dq), _p(dk), _p(dv), nseq, inner, outer_stride,
-                                                 inner_stride, seq_stride, heads, L, D, _stream()))
+def attn_small_bwd(q, k, v, do, dq, dk, dv, addr):
+    _chk_rows_bf16(q, k, v, do, dq, dk, dv)
+    native.check(native.lib().t2v_attn_small_bwd(_p(q), _p(k), _p(v), _p(do), _p(dq), _p(dk), _p(dv), *addr, _stream()))
     return dq, dk, dv
 
 

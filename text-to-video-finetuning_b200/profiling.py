@@ -1,0 +1,86 @@
+"""Measurement helpers shared by bench.py and tools/: record the argument template of every primitive call of one
+step, then time each distinct template as a CUDA graph of back-to-back launches (device time the graph-replayed step
+pays per launch, free of host launch latency; CUDA events on the launching stream)."""
+import collections
+
+import torch
+
+from . import prims
+
+
+def templ(x):
+    if torch.is_tensor(x):
+        return ("T", tuple(x.shape), str(x.dtype).replace("torch.", ""), tuple(x.stride()))
+    if isinstance(x, (tuple, list)):
+        return ("L", tuple(templ(v) for v in x))
+    return ("V", x)
+
+
+def build(t, dev):
+    kind = t[0]
+    if kind == "T":
+        shape, dt, stride = t[1], getattr(torch, t[2]), t[3]
+        span = 1 + sum((s - 1) * st for s, st in zip(shape, stride)) if all(s > 0 for s in shape) else 0
+        if dt == torch.int64:
+            base = torch.zeros(span, device=dev, dtype=dt)
+        else:
+            base = (torch.randn(span, device=dev) * 0.5).to(dt)
+        return torch.as_strided(base, shape, stride)
+    if kind == "L":
+        return tuple(build(v, dev) for v in t[1])
+    return t[1]
+
+
+def record_calls(run, names, work=None):
+    """Run `run()` once with prims.<names> hooked.  Returns OrderedDict template -> [count, work(name, args, kwargs)]."""
+    saved = {n: getattr(prims, n) for n in names}
+    calls = collections.OrderedDict()
+
+    def wrap(n, fn):
+        def inner(*a, **k):
+            key = (n, templ(a), tuple(sorted((kk, templ(v)) for kk, v in k.items())))
+            if key not in calls:
+                calls[key] = [0, work(n, a, k) if work else None]
+            calls[key][0] += 1
+            return fn(*a, **k)
+        return inner
+    for n in names:
+        setattr(prims, n, wrap(n, saved[n]))
+    try:
+        run()
+        torch.cuda.synchronize()
+    finally:
+        for n in names:
+            setattr(prims, n, saved[n])
+    return calls
+
+
+def replay_us(key, dev, reps=10, replays=3):
+    """Average device time (us) of one launch of the recorded call `key`, measured over a replayed CUDA graph."""
+    n, ta, tk = key
+    fn = getattr(prims, n)
+    a = build(ta, dev)
+    k = {kk: build(v, dev) for kk, v in tk}
+    fn(*a, **k)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn(*a, **k)
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(replays):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    us = 1e3 * e0.elapsed_time(e1) / (replays * reps)
+    del g, a, k
+    return us
+
+
+def prim_names():
+    skip = ("out_hw", "groupnorm_ws", "concat_channels", "split_channels")
+    return [n for n in dir(prims) if callable(getattr(prims, n)) and not n.startswith("_")
+            and getattr(getattr(prims, n), "__module__", "") == prims.__name__ and n not in skip]

@@ -58,7 +58,33 @@ class ParamArena:
                 if p.dim() >= 2:
                     p._t2v_shadow = self.shadow[o:o + n].view(ops._phys(view).shape)
         self.offsets = offs
+        self._attach_fused(module, {id(p): o for p, o in zip(self.params, offs)})
         self.refresh_shadow()
+
+    def _attach_fused(self, module, off_of):
+        """Attention projections registered back to back (to_q, to_k, to_v) are adjacent in the arena: expose them as
+        one [3C, in] (self-attention) or [2C, ctx] (cross-attention K|V) matrix so they run as a single GEMM."""
+        import torch.nn as nn
+        for m in module.modules():
+            if not all(type(getattr(m, a, None)) is nn.Linear for a in ("to_q", "to_k", "to_v")):
+                continue
+            ws = [m.to_q.weight, m.to_k.weight, m.to_v.weight]
+            if any(w.dim() != 2 or id(w) not in off_of or m_.bias is not None for w, m_ in zip(ws, (m.to_q, m.to_k, m.to_v))):
+                continue
+            o = [off_of[id(w)] for w in ws]
+            n = [w.numel() for w in ws]
+            group = None
+            if ws[0].shape == ws[1].shape == ws[2].shape and o[1] == o[0] + n[0] and o[2] == o[1] + n[1]:
+                group = ("qkv", ws, o[0])
+            elif ws[1].shape == ws[2].shape and o[2] == o[1] + n[1]:
+                group = ("kv", ws[1:], o[1])
+            if group is None:
+                continue
+            kind, params, start = group
+            rows, cin = sum(w.shape[0] for w in params), params[0].shape[1]
+            total = rows * cin
+            m._t2v_fused = (kind, ops.FusedWeight(params, self.shadow[start:start + total].view(rows, 1, 1, cin),
+                                                 self.grad[start:start + total].view(rows, 1, 1, cin)))
 
     def refresh_shadow(self):
         """fp32 master -> bf16 compute copy for every matrix parameter: one kernel over the flat buffer."""

@@ -23,24 +23,7 @@ from t2v_b200 import prims  # noqa: E402
 from t2v_b200 import step as S  # noqa: E402
 
 
-def templ(x):
-    if torch.is_tensor(x):
-        return ("T", tuple(x.shape), str(x.dtype).replace("torch.", ""))
-    if isinstance(x, (tuple, list)):
-        return ("L", tuple(templ(v) for v in x))
-    return ("V", x)
-
-
-def build(t, dev):
-    kind = t[0]
-    if kind == "T":
-        dt = getattr(torch, t[2])
-        if dt == torch.int64:
-            return torch.zeros(t[1], device=dev, dtype=dt)
-        return (torch.randn(t[1], device=dev) * 0.5).to(dt)
-    if kind == "L":
-        return tuple(build(v, dev) for v in t[1])
-    return t[1]
+from t2v_b200.profiling import prim_names, record_calls, replay_us  # noqa: E402
 
 
 def main():
@@ -57,56 +40,21 @@ def main():
     inputs = [x.to(dev) for x in bench.synthetic_inputs(1, bench.CFG2, 1234)]
     step(*inputs)
     torch.cuda.synchronize()
-    names = [n for n in dir(prims) if callable(getattr(prims, n)) and not n.startswith("_")
-             and getattr(getattr(prims, n), "__module__", "") == prims.__name__ and n not in ("out_hw", "groupnorm_ws", "concat_channels", "split_channels")]
-    saved = {n: getattr(prims, n) for n in names}
-    calls = collections.OrderedDict()
-
-    def wrap(n, fn):
-        def inner(*a, **k):
-            key = (n, templ(a), tuple(sorted((kk, templ(v)) for kk, v in k.items())))
-            if key not in calls:
-                calls[key] = [0, sig_and_work(n, a, k)]
-            calls[key][0] += 1
-            return fn(*a, **k)
-        return inner
-    for n in names:
-        setattr(prims, n, wrap(n, saved[n]))
-    step(*inputs)
-    torch.cuda.synchronize()
-    for n in names:
-        setattr(prims, n, saved[n])
+    calls = record_calls(lambda: step(*inputs), prim_names(), sig_and_work)
     del step, unet
     torch.cuda.empty_cache()
 
     rows = []
-    for (n, ta, tk), (cnt, (sig, fl, by)) in calls.items():
+    for key, (cnt, (sig, fl, by)) in calls.items():
+        n = key[0]
         if args.only and args.only not in n:
             continue
-        a = build(ta, dev)
-        k = {kk: build(v, dev) for kk, v in tk}
-        fn = saved[n]
         try:
-            fn(*a, **k)
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                for _ in range(args.reps):
-                    fn(*a, **k)
-            g.replay()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(3):
-                g.replay()
-            e1.record()
-            torch.cuda.synchronize()
-            us = 1e3 * e0.elapsed_time(e1) / (3 * args.reps)
+            us = replay_us(key, dev, args.reps)
         except Exception as ex:  # noqa: BLE001
             print("skip", n, sig, repr(ex)[:100])
             continue
         rows.append(dict(prim=n, sig=sig, us=us, n=cnt, flops=fl, bytes=by, ms_per_step=us * cnt / 1e3))
-        del a, k, g
     rows.sort(key=lambda r: -r["ms_per_step"])
     tot = sum(r["ms_per_step"] for r in rows)
     fam = collections.defaultdict(lambda: [0, 0.0, 0.0])
