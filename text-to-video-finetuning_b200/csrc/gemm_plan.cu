@@ -117,6 +117,7 @@ void apply_tiling(GemmParams& p, const Tiling& t) {
 // Split-K factor for accumulate-mode problems: minimise  waves(base_tiles * s) * (k-blocks per split * T_kblock + T_epilogue).
 int choose_splits(int64_t base_tiles, int kb_total) {
     const int sms = device_sm_count();
+    if (const int forced = env_int("T2V_FORCE_SPLITS")) return std::max(1, std::min(forced, kb_total));
     int best = 1;
     double best_cost = 1e30;
     for (int s = 1; s <= kb_total && s <= 128; ++s) {
@@ -336,17 +337,51 @@ int t2v_conv_wgrad(const void* x, const void* dy, float* dw, int32_t N, int32_t 
     p.tdim[1] = (Cout + kBlockM - 1) / kBlockM;
     p.tdim[2] = KW;
     p.tdim[3] = KH;
+    // Joint choice of (UMMA N, 128/256-row tiles, split-K factor).  Cost model fitted to a sweep over 14 weight-gradient
+    // shapes of the ms-1.7b UNet on B200 (tools/gemm_sweep.py, profiles/r1_wgrad_sweep.txt; picks within 1% of the best
+    // measured configuration on 13 of them): per k-block the slowest of tcgen05 issue, per-SM operand fill (~40 B/clk with
+    // MN-major boxes) and chip-wide L2->SM bandwidth (~6000 B/clk); the split-K epilogue pays for its red.global.add
+    // traffic at ~2500 B/clk chip-wide.
+    int splits = 1;
     {
-        // only the Cout tiles (variable 1) can pair up; taps and k-splits multiply the tile count.  The split factor is
-        // chosen afterwards, so model the main loop with the k-blocks a ~1-wave split would leave per tile.
-        const int rd[3] = {p.tdim[1], 1, 1};
+        const int sms = device_sm_count();
+        const int forced_bn = env_int("T2V_FORCE_BN"), forced_mh = env_int("T2V_FORCE_MH"), forced_s = env_int("T2V_FORCE_SPLITS");
         const int64_t taps = int64_t(KH) * KW;
-        const int kb_guess = std::max<int>(4, int(std::min<int64_t>(kb_total, kb_total * taps * p.tdim[1] * ((Cin + 159) / 160) / device_sm_count())));
-        apply_tiling(p, choose_tiling(rd, Cin, true, kb_guess, taps, true));
+        const int mt1 = p.tdim[1];
+        Tiling best{16, 1, -1};
+        double best_cost = 1e30;
+        for (int mh = 1; mh <= 2; ++mh) {
+            if ((forced_mh && mh != forced_mh) || (mh == 2 && mt1 < 2)) continue;
+            const int mt = mh == 2 ? (mt1 + 1) / 2 : mt1;
+            for (int bn = 256; bn >= 16; bn -= 16) {
+                if (forced_bn && bn != forced_bn) continue;
+                if (bn > 16 && bn - 16 >= Cin) continue;
+                const int stage_bytes = mh * kBlockM * 128 + ((bn + 63) / 64) * 8192;
+                const int budget = 232448 - 1024 - 256 - kEpilogueStagingBytes;
+                if (budget / stage_bytes < 3) continue;
+                const int64_t base = int64_t(mt) * ((Cin + bn - 1) / bn) * taps;
+                for (int s = 1; s <= kb_total && s <= 128; ++s) {
+                    if (forced_s && s != std::min(forced_s, kb_total)) continue;
+                    const int kper = (kb_total + s - 1) / s;
+                    if (!forced_s && (kb_total + kper - 1) / kper != s) continue;  // same schedule as a smaller s
+                    const int64_t tiles = base * s;
+                    const int64_t waves = (tiles + sms - 1) / sms;
+                    const double active = double(std::min<int64_t>(tiles, sms));
+                    const double t_kb = std::max({double(mh) * 2.0 * bn, stage_bytes / 40.0, stage_bytes * active / 6000.0, 260.0});
+                    const double t_epi = 500.0 + 4.0 * mh * bn;
+                    const double red = double(tiles) * mh * kBlockM * bn * 4.0 / 2500.0;
+                    const double cost = double(waves) * (kper * t_kb + t_epi) + red;
+                    if (cost < best_cost - 1e-9) {
+                        best_cost = cost;
+                        best = Tiling{bn, mh, mh == 2 ? 1 : -1};
+                        splits = s;
+                    }
+                }
+            }
+        }
+        apply_tiling(p, best);
     }
     p.tdim[0] = (Cin + p.block_n - 1) / p.block_n;
-    const int64_t base_tiles = int64_t(p.tdim[0]) * p.tdim[1] * KW * KH;
-    int splits = choose_splits(base_tiles, kb_total);
     p.kb_per_split = (kb_total + splits - 1) / splits;
     splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
     p.tdim[4] = splits;

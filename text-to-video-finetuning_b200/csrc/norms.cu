@@ -6,6 +6,7 @@
 // sample, C channels in G groups.  Statistics are reduced in two levels (pixel chunks -> sample) so the grid fills
 // the GPU even when S == 1.
 #include "common.h"
+#include "gemm_tc.cuh"
 #include "ptx.cuh"
 
 #include <algorithm>
@@ -25,48 +26,95 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 __device__ __forceinline__ float sigmoidf_(float z) { return 1.0f / (1.0f + __expf(-z)); }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm
-// Two kernels per direction (plus one memset of the [S][C][2] accumulator):
-//   gn_partial_kernel : per-channel sums over a chunk of pixels, reduced in shared memory, then ONE atomicAdd per
-//                       channel per block into accum[S][C][2].   MODE 0: (sum x, sum x^2); MODE 1: (sum dz, sum dz*xhat)
-//   gn_*_apply_kernel : every block first finalises its sample's statistics / coefficients from accum in shared memory
-//                       (2C..5C floats, fp64 for the group combine), then streams its own chunk of pixels.
-// Thread layout of the streaming loops: V = C/8 channel vectors; thread owns vector tid % V and pixel lane tid / V.
-template <int MODE>
-__global__ void gn_partial_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
-                                  const float* __restrict__ ab,   // [S][C][2] (a,b) for z = a x + b   (MODE 1)
-                                  const float* __restrict__ stat, // [S][G][2] (mean, rstd)            (MODE 1)
-                                  float* __restrict__ accum,      // [S][C][2]
-                                  int64_t P, int C, int G, int chunk_pixels, int silu) {
-    extern __shared__ float sh[];  // [2][C]
-    const int s = blockIdx.y, chunk = blockIdx.x;
-    const int V = C >> 3;
-    const int lanes = blockDim.x / V;
-    const int cv = threadIdx.x % V, pl = threadIdx.x / V;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+// ONE kernel per direction (plus one memset of the workspace): every block is resident at once (grid <= SMs x occupancy),
+// so the blocks of a sample can meet at a spin barrier between the two passes over their own pixels:
+//   pass 1  per-channel sums over the block's chunk of pixels, reduced in shared memory, one red.global.add per channel
+//           and block into accum[S][C][2]           fwd: (sum x, sum x^2)      bwd: (sum dz, sum dz*xhat)
+//   barrier per-sample arrival counter (workspace), bounded spin
+//   pass 2  every block finalises its sample's group statistics / coefficients from accum (fp64 group combine) and
+//           streams its chunk again - the second read hits L2 (the first pass just pulled it in)
+// Thread layout: V = C/8 channel vectors; thread owns vector tid % V (coefficients live in registers) and pixel lane
+// tid / V; loads are 16 bytes, 4 pixels in flight per thread.
+constexpr int kGnThreads = 512;
+
+struct GnArgs {
+    const __nv_bfloat16* x;
+    const __nv_bfloat16* dy;
+    const __nv_bfloat16* add;
+    __nv_bfloat16* out;       // y (fwd) / dx (bwd)
+    const float* gamma;
+    const float* beta;
+    float* stat;              // [S][G][2] (mean, rstd): written by fwd, read by bwd
+    float* ab;                // [S][C][2] (a, b) with z = a x + b: written by fwd, read by bwd
+    float* accum;             // [S][C][2] workspace, zeroed before launch
+    unsigned* arrive;         // [S] workspace, zeroed before launch
+    float* dgamma;
+    float* dbeta;
+    int64_t P;
+    int C, G, chunk_pixels, chunks, silu;
+    float eps;
+};
+
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ void gn_sample_barrier(unsigned* counter, unsigned target) {
     __syncthreads();
-    const int64_t p0 = int64_t(chunk) * chunk_pixels;
-    const int64_t p1 = min(P, p0 + chunk_pixels);
-    if (pl < lanes) {
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const uint64_t t0 = globaltimer_ns();
+        while (true) {
+            unsigned v;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if (v >= target) break;
+            __nanosleep(64);
+            if (globaltimer_ns() - t0 > 3000000000ull) __trap();  // a resident-grid assumption was violated
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kGnThreads, 1) gn_fused_kernel(const GnArgs g) {
+    extern __shared__ float sh[];  // [2][C] partial sums, then [2][G] group terms
+    const int C = g.C, G = g.G, cpg = C / G;
+    const int s = blockIdx.x / g.chunks, chunk = blockIdx.x % g.chunks;
+    const int V = C >> 3;
+    const int lanes = kGnThreads / V;
+    const int cv = threadIdx.x % V, pl = threadIdx.x / V;
+    const bool active = pl < lanes;
+    const int64_t p0 = int64_t(chunk) * g.chunk_pixels;
+    const int64_t p1 = min(g.P, p0 + g.chunk_pixels);
+    const uint4* xs = reinterpret_cast<const uint4*>(g.x + int64_t(s) * g.P * C) + cv;
+    const uint4* ds = MODE == 1 ? reinterpret_cast<const uint4*>(g.dy + int64_t(s) * g.P * C) + cv : nullptr;
+    for (int i = threadIdx.x; i < 2 * C; i += kGnThreads) sh[i] = 0.f;
+    __syncthreads();
+
+    float a[8], b[8];  // z = a x + b (bwd: read back from the forward pass; fwd: computed after the barrier)
+    float mean[8], rstd[8];
+    if (MODE == 1 && active) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = cv * 8 + j;
+            a[j] = g.ab[(int64_t(s) * C + c) * 2];
+            b[j] = g.ab[(int64_t(s) * C + c) * 2 + 1];
+            mean[j] = g.stat[(int64_t(s) * G + c / cpg) * 2];
+            rstd[j] = g.stat[(int64_t(s) * G + c / cpg) * 2 + 1];
+        }
+    }
+    // ---- pass 1
+    if (active) {
         float acc0[8], acc1[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc0[j] = acc1[j] = 0.f;
-        float a[8], b[8], mean[8], rstd[8];
-        if (MODE == 1) {
-            const int cpg = C / G;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int c = cv * 8 + j;
-                a[j] = ab[(int64_t(s) * C + c) * 2];
-                b[j] = ab[(int64_t(s) * C + c) * 2 + 1];
-                mean[j] = stat[(int64_t(s) * G + c / cpg) * 2];
-                rstd[j] = stat[(int64_t(s) * G + c / cpg) * 2 + 1];
-            }
-        }
-        const uint4* xs = reinterpret_cast<const uint4*>(x + (int64_t(s) * P) * C) + cv;
-        const uint4* ds = MODE == 1 ? reinterpret_cast<const uint4*>(dy + (int64_t(s) * P) * C) + cv : nullptr;
-        for (int64_t p = p0 + pl; p < p1; p += lanes) {
+        auto accumulate = [&](const uint4& qx, const uint4& qd) {
             float v[8];
-            unpack8(__ldg(xs + p * V), v);
+            unpack8(qx, v);
             if (MODE == 0) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -75,11 +123,11 @@ __global__ void gn_partial_kernel(const __nv_bfloat16* __restrict__ x, const __n
                 }
             } else {
                 float d[8];
-                unpack8(__ldg(ds + p * V), d);
+                unpack8(qd, d);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float dz = d[j];
-                    if (silu) {
+                    if (g.silu) {
                         const float z = a[j] * v[j] + b[j];
                         const float sg = sigmoidf_(z);
                         dz *= sg * (1.f + z * (1.f - sg));
@@ -88,6 +136,22 @@ __global__ void gn_partial_kernel(const __nv_bfloat16* __restrict__ x, const __n
                     acc1[j] += dz * (v[j] - mean[j]) * rstd[j];
                 }
             }
+        };
+        int64_t p = p0 + pl;
+        for (; p + 3 * lanes < p1; p += 4 * lanes) {
+            uint4 qx[4], qd[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                qx[u] = __ldg(xs + (p + u * lanes) * V);
+                if (MODE == 1) qd[u] = __ldg(ds + (p + u * lanes) * V);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) accumulate(qx[u], qd[u]);
+        }
+        for (; p < p1; p += lanes) {
+            uint4 qd = make_uint4(0, 0, 0, 0);
+            if (MODE == 1) qd = __ldg(ds + p * V);
+            accumulate(__ldg(xs + p * V), qd);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -96,145 +160,134 @@ __global__ void gn_partial_kernel(const __nv_bfloat16* __restrict__ x, const __n
         }
     }
     __syncthreads();
-    float* out = accum + int64_t(s) * C * 2;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        atomicAdd(out + 2 * c, sh[c]);
-        atomicAdd(out + 2 * c + 1, sh[C + c]);
+    float* acc = g.accum + int64_t(s) * C * 2;
+    for (int c = threadIdx.x; c < C; c += kGnThreads) {
+        atomicAdd(acc + 2 * c, sh[c]);
+        atomicAdd(acc + 2 * c + 1, sh[C + c]);
     }
-}
+    gn_sample_barrier(g.arrive + s, unsigned(g.chunks));
 
-// Forward apply: finalise (mean, rstd) per group and the per-channel affine (a, b) in shared memory, then y = act(a x + b).
-__global__ void gn_fwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ accum,
-                                    const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
-                                    float* __restrict__ stat, float* __restrict__ ab, int64_t P, int C, int G, int chunk_pixels,
-                                    float eps, int silu) {
-    extern __shared__ float sh[];  // a[C], b[C], gmean[G], grstd[G]
-    float* sa = sh;
-    float* sb = sh + C;
-    float* gm = sh + 2 * C;
-    float* gr = gm + G;
-    const int s = blockIdx.y;
-    const int cpg = C / G;
-    const float* acc = accum + int64_t(s) * C * 2;
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    // ---- finalise (every block, redundantly: 2C floats from L2)
+    float* t0 = sh;        // fwd: group mean   bwd: sum_c gamma * sum dz
+    float* t1 = sh + G;    // fwd: group rstd   bwd: sum_c gamma * sum dz*xhat
+    for (int gi = threadIdx.x; gi < G; gi += kGnThreads) {
         double a0 = 0, a1 = 0;
         for (int j = 0; j < cpg; ++j) {
-            a0 += acc[2 * (g * cpg + j)];
-            a1 += acc[2 * (g * cpg + j) + 1];
+            const int c = gi * cpg + j;
+            const float2 v = __ldcg(reinterpret_cast<const float2*>(acc) + c);
+            if (MODE == 0) {
+                a0 += v.x;
+                a1 += v.y;
+            } else {
+                a0 += double(g.gamma[c]) * v.x;
+                a1 += double(g.gamma[c]) * v.y;
+            }
         }
-        const double n = double(P) * cpg;
-        const double mean = a0 / n;
-        double var = a1 / n - mean * mean;
-        if (var < 0) var = 0;
-        const float rstd = float(1.0 / sqrt(var + double(eps)));
-        gm[g] = float(mean);
-        gr[g] = rstd;
-        if (blockIdx.x == 0) {
-            stat[(int64_t(s) * G + g) * 2] = float(mean);
-            stat[(int64_t(s) * G + g) * 2 + 1] = rstd;
-        }
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int g = c / cpg;
-        const float a = gr[g] * gamma[c];
-        const float b = beta[c] - gm[g] * a;
-        sa[c] = a;
-        sb[c] = b;
-        if (blockIdx.x == 0) {
-            ab[(int64_t(s) * C + c) * 2] = a;
-            ab[(int64_t(s) * C + c) * 2 + 1] = b;
-        }
-    }
-    __syncthreads();
-    const int V = C >> 3;
-    const int64_t p0 = int64_t(blockIdx.x) * chunk_pixels, p1 = min(P, p0 + chunk_pixels);
-    const int64_t nvec = (p1 - p0) * V;
-    const uint4* xs = reinterpret_cast<const uint4*>(x + (int64_t(s) * P + p0) * C);
-    uint4* ys = reinterpret_cast<uint4*>(y + (int64_t(s) * P + p0) * C);
-    for (int64_t i = threadIdx.x; i < nvec; i += blockDim.x) {
-        const int cv = int(i % V);
-        float v[8];
-        unpack8(__ldg(xs + i), v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float z = sa[cv * 8 + j] * v[j] + sb[cv * 8 + j];
-            if (silu) z *= sigmoidf_(z);
-            v[j] = z;
-        }
-        ys[i] = pack8(v);
-    }
-}
-
-// Backward apply: dx = pc * dz + qc * x + rc (+ add), dz = dy * silu'(a x + b); block 0 of each sample also
-// accumulates dgamma / dbeta.
-__global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
-                                    const float* __restrict__ accum, const float* __restrict__ gamma, const float* __restrict__ stat,
-                                    const float* __restrict__ ab, const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ dx,
-                                    float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t P, int C, int G, int chunk_pixels,
-                                    int silu) {
-    extern __shared__ float sh[];  // pc[C], qc[C], rc[C], a[C], b[C], s1[G], s2[G]
-    float* pc = sh;
-    float* qc = sh + C;
-    float* rc = sh + 2 * C;
-    float* sa = sh + 3 * C;
-    float* sb = sh + 4 * C;
-    float* g1 = sh + 5 * C;
-    float* g2 = g1 + G;
-    const int s = blockIdx.y;
-    const int cpg = C / G;
-    const float* acc = accum + int64_t(s) * C * 2;  // (sum dz, sum dz*xhat) per channel
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
-        double s1 = 0, s2 = 0;
-        for (int j = 0; j < cpg; ++j) {
-            const int c = g * cpg + j;
-            s1 += double(gamma[c]) * acc[2 * c];
-            s2 += double(gamma[c]) * acc[2 * c + 1];
-        }
-        g1[g] = float(s1);
-        g2[g] = float(s2);
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int g = c / cpg;
-        const float mean = stat[(int64_t(s) * G + g) * 2], rstd = stat[(int64_t(s) * G + g) * 2 + 1];
-        const float invn = 1.0f / (float(P) * cpg);
-        const float q = -rstd * rstd * g2[g] * invn;
-        pc[c] = rstd * gamma[c];
-        qc[c] = q;
-        rc[c] = -rstd * g1[g] * invn - q * mean;
-        sa[c] = ab[(int64_t(s) * C + c) * 2];
-        sb[c] = ab[(int64_t(s) * C + c) * 2 + 1];
-        if (blockIdx.x == 0) {
-            if (dbeta) atomicAdd(dbeta + c, acc[2 * c]);
-            if (dgamma) atomicAdd(dgamma + c, acc[2 * c + 1]);
+        if (MODE == 0) {
+            const double n = double(g.P) * cpg;
+            const double m = a0 / n;
+            double var = a1 / n - m * m;
+            if (var < 0) var = 0;
+            const float r = float(1.0 / sqrt(var + double(g.eps)));
+            t0[gi] = float(m);
+            t1[gi] = r;
+            if (chunk == 0) {
+                g.stat[(int64_t(s) * G + gi) * 2] = float(m);
+                g.stat[(int64_t(s) * G + gi) * 2 + 1] = r;
+            }
+        } else {
+            t0[gi] = float(a0);
+            t1[gi] = float(a1);
         }
     }
     __syncthreads();
-    const int V = C >> 3;
-    const int64_t p0 = int64_t(blockIdx.x) * chunk_pixels, p1 = min(P, p0 + chunk_pixels);
-    const int64_t nvec = (p1 - p0) * V;
-    const int64_t base = (int64_t(s) * P + p0) * V;
-    for (int64_t i = threadIdx.x; i < nvec; i += blockDim.x) {
-        const int cv = int(i % V);
-        float v[8], d[8], r[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(x) + base + i), v);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dy) + base + i), d);
-        if (add) unpack8(__ldg(reinterpret_cast<const uint4*>(add) + base + i), r);
+    if (chunk == 0) {
+        for (int c = threadIdx.x; c < C; c += kGnThreads) {
+            if (MODE == 0) {
+                const float aa = t1[c / cpg] * g.gamma[c];
+                g.ab[(int64_t(s) * C + c) * 2] = aa;
+                g.ab[(int64_t(s) * C + c) * 2 + 1] = g.beta[c] - t0[c / cpg] * aa;
+            } else {
+                const float2 v = __ldcg(reinterpret_cast<const float2*>(acc) + c);
+                if (g.dbeta) atomicAdd(g.dbeta + c, v.x);
+                if (g.dgamma) atomicAdd(g.dgamma + c, v.y);
+            }
+        }
+    }
+    if (!active) return;
+    // ---- pass 2
+    uint4* os = reinterpret_cast<uint4*>(g.out + int64_t(s) * g.P * C) + cv;
+    if (MODE == 0) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = cv * 8 + j;
-            float dz = d[j];
-            if (silu) {
-                const float z = sa[c] * v[j] + sb[c];
-                const float sg = sigmoidf_(z);
-                dz *= sg * (1.f + z * (1.f - sg));
-            }
-            float o = pc[c] * dz + qc[c] * v[j] + rc[c];
-            if (add) o += r[j];
-            v[j] = o;
+            a[j] = t1[c / cpg] * g.gamma[c];
+            b[j] = g.beta[c] - t0[c / cpg] * a[j];
         }
-        reinterpret_cast<uint4*>(dx)[base + i] = pack8(v);
+        auto apply = [&](const uint4& qx) {
+            float v[8];
+            unpack8(qx, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float z = a[j] * v[j] + b[j];
+                if (g.silu) z *= sigmoidf_(z);
+                v[j] = z;
+            }
+            return pack8(v);
+        };
+        int64_t p = p0 + pl;
+        for (; p + 3 * lanes < p1; p += 4 * lanes) {
+            uint4 qx[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) qx[u] = __ldg(xs + (p + u * lanes) * V);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) os[(p + u * lanes) * V] = apply(qx[u]);
+        }
+        for (; p < p1; p += lanes) os[p * V] = apply(__ldg(xs + p * V));
+    } else {
+        // dx = pc * dz + qc * x + rc (+ add)
+        float pc[8], qc[8], rc[8];
+        const float invn = 1.0f / (float(g.P) * cpg);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = cv * 8 + j;
+            const float q = -rstd[j] * rstd[j] * t1[c / cpg] * invn;
+            pc[j] = rstd[j] * g.gamma[c];
+            qc[j] = q;
+            rc[j] = -rstd[j] * t0[c / cpg] * invn - q * mean[j];
+        }
+        const uint4* as = g.add ? reinterpret_cast<const uint4*>(g.add + int64_t(s) * g.P * C) + cv : nullptr;
+        auto apply = [&](const uint4& qx, const uint4& qd, const uint4& qa) {
+            float v[8], d[8], r[8];
+            unpack8(qx, v);
+            unpack8(qd, d);
+            unpack8(qa, r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float dz = d[j];
+                if (g.silu) {
+                    const float z = a[j] * v[j] + b[j];
+                    const float sg = sigmoidf_(z);
+                    dz *= sg * (1.f + z * (1.f - sg));
+                }
+                v[j] = pc[j] * dz + qc[j] * v[j] + rc[j] + r[j];
+            }
+            return pack8(v);
+        };
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+        int64_t p = p0 + pl;
+        for (; p + lanes < p1; p += 2 * lanes) {
+            uint4 qx[2], qd[2], qa[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                qx[u] = __ldg(xs + (p + u * lanes) * V);
+                qd[u] = __ldg(ds + (p + u * lanes) * V);
+                qa[u] = as ? __ldg(as + (p + u * lanes) * V) : zero;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) os[(p + u * lanes) * V] = apply(qx[u], qd[u], qa[u]);
+        }
+        for (; p < p1; p += lanes) os[p * V] = apply(__ldg(xs + p * V), __ldg(ds + p * V), as ? __ldg(as + p * V) : zero);
     }
 }
 
@@ -379,29 +432,46 @@ __global__ void ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bf
     }
 }
 
-static int gn_block(int C) {
-    const int V = C / 8;
-    int b = 256;
-    while (b < V) b += 32;
-    return b;
+// Blocks that can be resident at once (the spin barrier needs the whole grid on the chip).
+static int gn_resident_blocks() {
+    static int cached = 0;
+    if (cached) return cached;
+    cudaFuncSetAttribute(gn_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(gn_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    int per_sm0 = 0, per_sm1 = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm0, gn_fused_kernel<0>, kGnThreads, 64 * 1024);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, gn_fused_kernel<1>, kGnThreads, 64 * 1024);
+    cached = std::max(1, std::min(per_sm0, per_sm1)) * device_sm_count();
+    return cached;
 }
 
-static void gn_chunks(int S, int64_t P, int& chunk_pixels, int& chunks) {
-    // aim for ~4 blocks per SM overall; small problems get small chunks (>= 4 pixels) so they still spread over SMs
-    const int64_t want = std::max<int64_t>(1, (4 * 148 + S - 1) / S);
-    int64_t cp = std::max<int64_t>(4, (P + want - 1) / want);
+static int gn_plan(int S, int64_t P, int C, int& chunk_pixels, int& chunks) {
+    const int resident = gn_resident_blocks();
+    if (S > resident) return -1;
+    const int lanes = kGnThreads / (C / 8);
+    // one block per SM overall, each with at least one pixel per lane (and >= 2 pixels) so tiny maps still spread out
+    const int64_t want = std::max<int64_t>(1, resident / S);
+    const int64_t min_px = std::max<int64_t>(2, lanes);
+    const int64_t cp = std::max<int64_t>(min_px, (P + want - 1) / want);
     chunk_pixels = int(std::min<int64_t>(cp, P));
     chunks = int((P + chunk_pixels - 1) / chunk_pixels);
+    return 0;
 }
 
-static void gn_set_attrs() {
-    static bool done = false;
-    if (done) return;
-    cudaFuncSetAttribute(gn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute(gn_fwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(gn_partial_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(gn_partial_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    done = true;
+static size_t gn_accum_bytes(int S, int C) { return (size_t(S) * C * 2 * sizeof(float) + 255) / 256 * 256; }
+
+template <int MODE>
+static int gn_launch(GnArgs& g, void* workspace, int S, cudaStream_t st) {
+    if (g.C % 8 || g.C % g.G || g.C / 8 > kGnThreads || 2 * g.C * sizeof(float) > 64 * 1024)
+        return fail(-2, "groupnorm: C=%d G=%d unsupported", g.C, g.G);
+    if (gn_plan(S, g.P, g.C, g.chunk_pixels, g.chunks)) return fail(-2, "groupnorm: %d samples exceed the resident grid", S);
+    const size_t ab = gn_accum_bytes(S, g.C);
+    g.accum = static_cast<float*>(workspace);
+    g.arrive = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + ab);
+    cudaMemsetAsync(workspace, 0, ab + size_t(S) * sizeof(unsigned), st);
+    gn_fused_kernel<MODE><<<S * g.chunks, kGnThreads, std::max<size_t>(2 * g.C, 2 * g.G) * sizeof(float), st>>>(g);
+    count_launch(1);
+    return 0;
 }
 
 }  // namespace t2v
@@ -412,44 +482,32 @@ extern "C" {
 
 int64_t t2v_groupnorm_workspace_bytes(int32_t S, int64_t P, int32_t C) {
     (void)P;
-    return int64_t(S) * C * 2 * sizeof(float) + 256;
+    return int64_t(gn_accum_bytes(S, C)) + int64_t(S) * sizeof(unsigned) + 256;
 }
 
 int t2v_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stat, float* ab, void* workspace,
                       int32_t S, int64_t P, int32_t C, int32_t G, float eps, int32_t silu, void* stream_) {
-    if (C % 8 || C % G || C / 8 > 1024) return fail(-2, "groupnorm: C=%d G=%d unsupported", C, G);
-    cudaStream_t st = static_cast<cudaStream_t>(stream_);
-    gn_set_attrs();
-    int cp, chunks;
-    gn_chunks(S, P, cp, chunks);
-    float* accum = static_cast<float*>(workspace);
-    cudaMemsetAsync(accum, 0, size_t(S) * C * 2 * sizeof(float), st);
-    const int bs = gn_block(C);
-    gn_partial_kernel<0><<<dim3(chunks, S), bs, 2 * C * sizeof(float), st>>>(
-        static_cast<const __nv_bfloat16*>(x), nullptr, nullptr, nullptr, accum, P, C, G, cp, 0);
-    gn_fwd_apply_kernel<<<dim3(chunks, S), 256, (2 * C + 2 * G) * sizeof(float), st>>>(
-        static_cast<const __nv_bfloat16*>(x), accum, gamma, beta, static_cast<__nv_bfloat16*>(y), stat, ab, P, C, G, cp, eps, silu);
-    count_launch(1);
+    GnArgs g{};
+    g.x = static_cast<const __nv_bfloat16*>(x);
+    g.out = static_cast<__nv_bfloat16*>(y);
+    g.gamma = gamma; g.beta = beta; g.stat = stat; g.ab = ab;
+    g.P = P; g.C = C; g.G = G; g.silu = silu; g.eps = eps;
+    if (int r = gn_launch<0>(g, workspace, S, static_cast<cudaStream_t>(stream_))) return r;
     return launch_checked(int(cudaGetLastError()), "groupnorm_fwd");
 }
 
 int t2v_groupnorm_bwd(const void* dy, const void* x, const float* gamma, const float* stat, const float* ab, const void* add,
                       void* dx, float* dgamma, float* dbeta, void* workspace, int32_t S, int64_t P, int32_t C, int32_t G,
                       int32_t silu, void* stream_) {
-    if (C % 8 || C % G || C / 8 > 1024) return fail(-2, "groupnorm: C=%d G=%d unsupported", C, G);
-    cudaStream_t st = static_cast<cudaStream_t>(stream_);
-    gn_set_attrs();
-    int cp, chunks;
-    gn_chunks(S, P, cp, chunks);
-    float* accum = static_cast<float*>(workspace);
-    cudaMemsetAsync(accum, 0, size_t(S) * C * 2 * sizeof(float), st);
-    const int bs = gn_block(C);
-    gn_partial_kernel<1><<<dim3(chunks, S), bs, 2 * C * sizeof(float), st>>>(
-        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), ab, stat, accum, P, C, G, cp, silu);
-    gn_bwd_apply_kernel<<<dim3(chunks, S), 256, (5 * C + 2 * G) * sizeof(float), st>>>(
-        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), accum, gamma, stat, ab,
-        static_cast<const __nv_bfloat16*>(add), static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, P, C, G, cp, silu);
-    count_launch(1);
+    GnArgs g{};
+    g.x = static_cast<const __nv_bfloat16*>(x);
+    g.dy = static_cast<const __nv_bfloat16*>(dy);
+    g.add = static_cast<const __nv_bfloat16*>(add);
+    g.out = static_cast<__nv_bfloat16*>(dx);
+    g.gamma = gamma; g.stat = const_cast<float*>(stat); g.ab = const_cast<float*>(ab);
+    g.dgamma = dgamma; g.dbeta = dbeta;
+    g.P = P; g.C = C; g.G = G; g.silu = silu;
+    if (int r = gn_launch<1>(g, workspace, S, static_cast<cudaStream_t>(stream_))) return r;
     return launch_checked(int(cudaGetLastError()), "groupnorm_bwd");
 }
 
