@@ -50,6 +50,7 @@ template <int D>
 __global__ void attn_small_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                                       const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ o, SeqAddr a, int64_t nseq,
                                       int heads, int L, float scale) {
+    pdl_sync();
     extern __shared__ float sm_all[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = L * (D + 1);  // shared memory is sized by the actual sequence length (occupancy)
@@ -109,6 +110,7 @@ __global__ void attn_small_bwd_kernel(const __nv_bfloat16* __restrict__ q, const
                                       const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ dout,
                                       __nv_bfloat16* __restrict__ dq, __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv,
                                       SeqAddr a, int64_t nseq, int heads, int L, float scale) {
+    pdl_sync();
     extern __shared__ float sm_all[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = L * (D + 1);
@@ -251,8 +253,8 @@ int t2v_attn_small_fwd(const void* q, const void* k, const void* v, void* o, int
     auto V = static_cast<const __nv_bfloat16*>(v);
     auto O = static_cast<__nv_bfloat16*>(o);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (D == 64) attn_small_fwd_kernel<64><<<grid, warps * 32, smem, st>>>(Q, K, V, O, a, nseq, heads, L, scale);
-    else attn_small_fwd_kernel<32><<<grid, warps * 32, smem, st>>>(Q, K, V, O, a, nseq, heads, L, scale);
+    if (D == 64) launch_pdl(attn_small_fwd_kernel<64>, dim3(grid), dim3(warps * 32), size_t(smem), st, Q, K, V, O, a, nseq, heads, L, scale);
+    else launch_pdl(attn_small_fwd_kernel<32>, dim3(grid), dim3(warps * 32), size_t(smem), st, Q, K, V, O, a, nseq, heads, L, scale);
     return launch_checked(int(cudaGetLastError()), "attn_small_fwd");
 }
 
@@ -278,8 +280,8 @@ int t2v_attn_small_bwd(const void* q, const void* k, const void* v, const void* 
     auto B = [](const void* p) { return static_cast<const __nv_bfloat16*>(p); };
     auto W = [](void* p) { return static_cast<__nv_bfloat16*>(p); };
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (D == 64) attn_small_bwd_kernel<64><<<grid, warps * 32, smem, st>>>(B(q), B(k), B(v), B(dout), W(dq), W(dk), W(dv), a, nseq, heads, L, scale);
-    else attn_small_bwd_kernel<32><<<grid, warps * 32, smem, st>>>(B(q), B(k), B(v), B(dout), W(dq), W(dk), W(dv), a, nseq, heads, L, scale);
+    if (D == 64) launch_pdl(attn_small_bwd_kernel<64>, dim3(grid), dim3(warps * 32), size_t(smem), st, B(q), B(k), B(v), B(dout), W(dq), W(dk), W(dv), a, nseq, heads, L, scale);
+    else launch_pdl(attn_small_bwd_kernel<32>, dim3(grid), dim3(warps * 32), size_t(smem), st, B(q), B(k), B(v), B(dout), W(dq), W(dk), W(dv), a, nseq, heads, L, scale);
     return launch_checked(int(cudaGetLastError()), "attn_small_bwd");
 }
 

@@ -1,5 +1,7 @@
 #include "common.h"
 
+#include <cstdlib>
+
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -30,6 +32,10 @@ int launch_checked(int cuda_err, const char* what) {
 const char* last_error() { return g_err; }
 int64_t launches() { return g_launches.load(std::memory_order_relaxed); }
 
+bool pdl_enabled() {
+    static const bool on = std::getenv("T2V_NO_PDL") == nullptr;
+    return on;
+}
 }  // namespace t2v
 
 namespace t2v {

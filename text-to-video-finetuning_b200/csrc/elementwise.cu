@@ -34,6 +34,7 @@ static inline int ew_grid(int64_t n, int threads = 256) {
 //   x_t = sqrt(abar[t_b]) x0 + sqrt(1 - abar[t_b]) eps        (train.py:760)
 __global__ void to_nhwc8_kernel(const float* __restrict__ x0, const float* __restrict__ noise, const float* __restrict__ abar,
                                 const int64_t* __restrict__ t, __nv_bfloat16* __restrict__ out, int B, int C, int F, int HW) {
+    pdl_sync();
     const int64_t npix = int64_t(B) * F * HW;
     GRID_STRIDE(i, npix) {
         const int hw = int(i % HW);
@@ -62,6 +63,7 @@ __global__ void to_nhwc8_kernel(const float* __restrict__ x0, const float* __res
 
 // [B*F][H][W][8] bf16 -> (B, C, F, H, W) fp32
 __global__ void from_nhwc8_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int B, int C, int F, int HW) {
+    pdl_sync();
     const int64_t npix = int64_t(B) * F * HW;
     GRID_STRIDE(i, npix) {
         const int hw = int(i % HW);
@@ -77,6 +79,7 @@ __global__ void from_nhwc8_kernel(const __nv_bfloat16* __restrict__ in, float* _
 // MSE forward: loss += sum (pred - target)^2 / numel ; backward: dpred = g * 2 (pred - target) / numel
 __global__ void mse_kernel(const __nv_bfloat16* __restrict__ pred, const float* __restrict__ target, float* __restrict__ loss,
                            const float* __restrict__ gout, __nv_bfloat16* __restrict__ dpred, int B, int C, int F, int HW) {
+    pdl_sync();
     const int64_t npix = int64_t(B) * F * HW;
     const float inv = 1.0f / (float(npix) * C);
     const float g = (dpred && gout) ? *gout : 1.0f;
@@ -114,6 +117,7 @@ __global__ void mse_kernel(const __nv_bfloat16* __restrict__ pred, const float* 
 // ------------------------------------------------------------------------------------------------ activations
 // GEGLU: proj [M][2I] -> out [M][I] = h * gelu(gate)   (diffusers GEGLU; exact erf GELU)
 __global__ void geglu_fwd_kernel(const __nv_bfloat16* __restrict__ proj, __nv_bfloat16* __restrict__ out, int64_t M, int I) {
+    pdl_sync();
     const int V = I >> 3;
     GRID_STRIDE(i, M * V) {
         const int64_t m = i / V;
@@ -129,6 +133,7 @@ __global__ void geglu_fwd_kernel(const __nv_bfloat16* __restrict__ proj, __nv_bf
 }
 __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ proj, const __nv_bfloat16* __restrict__ dout,
                                  __nv_bfloat16* __restrict__ dproj, int64_t M, int I) {
+    pdl_sync();
     const int V = I >> 3;
     GRID_STRIDE(i, M * V) {
         const int64_t m = i / V;
@@ -151,6 +156,7 @@ __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ proj, const _
 
 // SiLU on a small fp32 tensor (time embedding path): y_bf16 = silu(x_f32);  backward: dx_f32 = dy_f32 * silu'(x)
 __global__ void silu_f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n, int apply) {
+    pdl_sync();
     GRID_STRIDE(i, n) {
         const float v = x[i];
         y[i] = __float2bfloat16_rn(apply ? v * sigm(v) : v);
@@ -158,6 +164,7 @@ __global__ void silu_f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat
 }
 __global__ void silu_bwd_f32_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int64_t n,
                                     int accumulate) {
+    pdl_sync();
     GRID_STRIDE(i, n) {
         const float v = x[i], s = sigm(v);
         const float g = dy[i] * s * (1.f + v * (1.f - s));
@@ -166,6 +173,7 @@ __global__ void silu_bwd_f32_kernel(const float* __restrict__ x, const float* __
 }
 
 __global__ void silu_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
+    pdl_sync();
     GRID_STRIDE(i, n) {
         const float v = __bfloat162float(x[i]);
         y[i] = __float2bfloat16_rn(v * sigm(v));
@@ -173,6 +181,7 @@ __global__ void silu_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloa
 }
 __global__ void silu_bf16_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                      __nv_bfloat16* __restrict__ dx, int64_t n) {
+    pdl_sync();
     GRID_STRIDE(i, n) {
         const float v = __bfloat162float(x[i]), s = sigm(v);
         dx[i] = __float2bfloat16_rn(__bfloat162float(dy[i]) * s * (1.f + v * (1.f - s)));
@@ -182,6 +191,7 @@ __global__ void silu_bf16_bwd_kernel(const __nv_bfloat16* __restrict__ x, const 
 // out = a + b (+ c)   (gradient fan-in)
 __global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                            const __nv_bfloat16* __restrict__ c, __nv_bfloat16* __restrict__ out, int64_t nvec) {
+    pdl_sync();
     GRID_STRIDE(i, nvec) {
         float x[8], y[8];
         unpack8e(__ldg(reinterpret_cast<const uint4*>(a) + i), x);
@@ -197,6 +207,7 @@ __global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloa
     }
 }
 __global__ void scale_bf16_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ out, int64_t nvec, float alpha) {
+    pdl_sync();
     GRID_STRIDE(i, nvec) {
         float x[8];
         unpack8e(__ldg(reinterpret_cast<const uint4*>(a) + i), x);
@@ -206,10 +217,12 @@ __global__ void scale_bf16_kernel(const __nv_bfloat16* __restrict__ a, __nv_bflo
     }
 }
 __global__ void add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t n) {
+    pdl_sync();
     GRID_STRIDE(i, n) out[i] = a[i] + b[i];
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+    pdl_sync();
     const int64_t nv = n >> 3;
     GRID_STRIDE(i, nv) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
@@ -224,6 +237,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
 // nearest-neighbour resize [N][H][W][C] -> [N][Ho][Wo][C]  (src = floor(dst * in / out), F.interpolate 'nearest')
 __global__ void upsample_nearest_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
                                             int W, int Ho, int Wo, int C) {
+    pdl_sync();
     const int V = C >> 3;
     const int64_t total = int64_t(N) * Ho * Wo * V;
     GRID_STRIDE(i, total) {
@@ -240,6 +254,7 @@ __global__ void upsample_nearest_fwd_kernel(const __nv_bfloat16* __restrict__ x,
 // backward of the nearest resize: dx[h][w] = sum of dy over the output pixels that read (h, w)
 __global__ void upsample_nearest_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int N, int H,
                                             int W, int Ho, int Wo, int C) {
+    pdl_sync();
     const int V = C >> 3;
     const int64_t total = int64_t(N) * H * W * V;
     GRID_STRIDE(i, total) {
@@ -267,6 +282,7 @@ __global__ void upsample_nearest_bwd_kernel(const __nv_bfloat16* __restrict__ dy
 // strided 2-D copy of bf16 rows: dst[m][dst_off + c] = src[m][src_off + c], c < C  (concat / split of channels)
 __global__ void copy_cols_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t M, int C,
                                  int src_ld, int src_off, int dst_ld, int dst_off) {
+    pdl_sync();
     const int V = C >> 3;
     GRID_STRIDE(i, M * V) {
         const int64_t m = i / V;
@@ -279,7 +295,8 @@ __global__ void copy_cols_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfl
 // ------------------------------------------------------------------------------------------------ reductions
 // Segmented column sum: out[s][c] (+)= sum_p x[s][p][c].  Grid (chunks, S); per-thread 8-channel vectors.
 __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int64_t P, int C, int chunk_rows,
-                              int ld, int col0) {  // C = width of this column block, ld = full row length, col0 = first column
+                              int ld, int col0) {
+    pdl_sync();  // C = width of this column block, ld = full row length, col0 = first column
     extern __shared__ float sh[];  // [C]
     const int s = blockIdx.y;
     const int V = C >> 3;
@@ -306,6 +323,7 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __rest
 }
 // out[c] += sum_s x[s][c] for a small fp32 matrix
 __global__ void colsum_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int S, int C) {
+    pdl_sync();
     GRID_STRIDE(c, C) {
         float a = 0.f;
         for (int s = 0; s < S; ++s) a += x[int64_t(s) * C + c];
@@ -316,6 +334,7 @@ __global__ void colsum_f32_kernel(const float* __restrict__ x, float* __restrict
 // Row softmax over fp32 scores -> bf16 probabilities; columns >= n_valid (padding up to ld_out) are written as 0.
 __global__ void softmax_fwd_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, int64_t rows, int n_valid, int ld_in,
                                    int ld_out) {
+    pdl_sync();
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
     const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
@@ -337,6 +356,7 @@ __global__ void softmax_fwd_kernel(const float* __restrict__ s, __nv_bfloat16* _
 // dS = P * (dP - rowsum(dP * P)) * scale  -> bf16 (padding columns zero)
 __global__ void softmax_bwd_kernel(const __nv_bfloat16* __restrict__ p, const float* __restrict__ dp, __nv_bfloat16* __restrict__ ds,
                                    int64_t rows, int n_valid, int ld_p, int ld_dp, float scale) {
+    pdl_sync();
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
     const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
@@ -363,6 +383,7 @@ __device__ __forceinline__ uint32_t mix32(uint64_t seed, uint64_t idx) {
 }
 __global__ void dropout_scale_add_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ base,
                                          __nv_bfloat16* __restrict__ out, int64_t nvec, float p, float scale, uint64_t seed) {
+    pdl_sync();
     const uint32_t thresh = uint32_t(double(p) * 4294967296.0);
     const float k = scale / (1.f - p);
     GRID_STRIDE(i, nvec) {
@@ -382,6 +403,7 @@ __global__ void dropout_scale_add_kernel(const __nv_bfloat16* __restrict__ x, co
 // moments [B*F][HW][8] bf16 (mean = ch 0..3, logvar = ch 4..7)  ->  latents (B, 4, F, HW) fp32
 __global__ void vae_sample_kernel(const __nv_bfloat16* __restrict__ mom, const float* __restrict__ eps, float* __restrict__ out,
                                   int B, int F, int HW, float scale) {
+    pdl_sync();
     const int64_t npix = int64_t(B) * F * HW;
     GRID_STRIDE(i, npix) {
         const int hw = int(i % HW);
@@ -400,6 +422,7 @@ __global__ void vae_sample_kernel(const __nv_bfloat16* __restrict__ mom, const f
 
 // Timesteps(dim, flip_sin_to_cos=True, shift=0): [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(10000) i / half)  -> bf16 [B][dim]
 __global__ void timestep_embed_kernel(const int64_t* __restrict__ t, __nv_bfloat16* __restrict__ out, int B, int dim) {
+    pdl_sync();
     const int half = dim >> 1;
     GRID_STRIDE(i, int64_t(B) * half) {
         const int b = int(i / half), k = int(i % half);
@@ -423,79 +446,79 @@ int t2v_latents_to_nhwc8(const float* x0, const float* noise, const float* alpha
                          int32_t B, int32_t C, int32_t F, int32_t HW, void* stream) {
     if (C > 8) return fail(-2, "latents_to_nhwc8: C=%d > 8", C);
     const int64_t n = int64_t(B) * F * HW;
-    to_nhwc8_kernel<<<ew_grid(n), 256, 0, ST>>>(x0, noise, alphas_cumprod, timesteps, BFW(out), B, C, F, HW);
+    launch_pdl(to_nhwc8_kernel, dim3(ew_grid(n)), dim3(256), size_t(0), ST, x0, noise, alphas_cumprod, timesteps, BFW(out), B, C, F, HW);
     return launch_checked(int(cudaGetLastError()), "latents_to_nhwc8");
 }
 int t2v_nhwc8_to_latents(const void* in, float* out, int32_t B, int32_t C, int32_t F, int32_t HW, void* stream) {
     const int64_t n = int64_t(B) * F * HW;
-    from_nhwc8_kernel<<<ew_grid(n), 256, 0, ST>>>(BF(in), out, B, C, F, HW);
+    launch_pdl(from_nhwc8_kernel, dim3(ew_grid(n)), dim3(256), size_t(0), ST, BF(in), out, B, C, F, HW);
     return launch_checked(int(cudaGetLastError()), "nhwc8_to_latents");
 }
 int t2v_mse_loss(const void* pred, const float* target, float* loss, const float* gout, void* dpred, int32_t B, int32_t C,
                  int32_t F, int32_t HW, void* stream) {
     const int64_t n = int64_t(B) * F * HW;
     if (loss) cudaMemsetAsync(loss, 0, sizeof(float), ST);
-    mse_kernel<<<ew_grid(n), 256, 0, ST>>>(BF(pred), target, loss, gout, BFW(dpred), B, C, F, HW);
+    launch_pdl(mse_kernel, dim3(ew_grid(n)), dim3(256), size_t(0), ST, BF(pred), target, loss, gout, BFW(dpred), B, C, F, HW);
     return launch_checked(int(cudaGetLastError()), "mse_loss");
 }
 int t2v_geglu_fwd(const void* proj, void* out, int64_t M, int32_t I, void* stream) {
     if (I % 8) return fail(-2, "geglu: inner dim %d not a multiple of 8", I);
-    geglu_fwd_kernel<<<ew_grid(M * (I / 8)), 256, 0, ST>>>(BF(proj), BFW(out), M, I);
+    launch_pdl(geglu_fwd_kernel, dim3(ew_grid(M * (I / 8))), dim3(256), size_t(0), ST, BF(proj), BFW(out), M, I);
     return launch_checked(int(cudaGetLastError()), "geglu_fwd");
 }
 int t2v_geglu_bwd(const void* proj, const void* dout, void* dproj, int64_t M, int32_t I, void* stream) {
     if (I % 8) return fail(-2, "geglu: inner dim %d not a multiple of 8", I);
-    geglu_bwd_kernel<<<ew_grid(M * (I / 8)), 256, 0, ST>>>(BF(proj), BF(dout), BFW(dproj), M, I);
+    launch_pdl(geglu_bwd_kernel, dim3(ew_grid(M * (I / 8))), dim3(256), size_t(0), ST, BF(proj), BF(dout), BFW(dproj), M, I);
     return launch_checked(int(cudaGetLastError()), "geglu_bwd");
 }
 int t2v_silu_f32_to_bf16(const float* x, void* y, int64_t n, int32_t apply_silu, void* stream) {
-    silu_f32_to_bf16_kernel<<<ew_grid(n), 256, 0, ST>>>(x, BFW(y), n, apply_silu);
+    launch_pdl(silu_f32_to_bf16_kernel, dim3(ew_grid(n)), dim3(256), size_t(0), ST, x, BFW(y), n, apply_silu);
     return launch_checked(int(cudaGetLastError()), "silu_f32_to_bf16");
 }
 int t2v_silu_bwd_f32(const float* x, const float* dy, float* dx, int64_t n, int32_t accumulate, void* stream) {
-    silu_bwd_f32_kernel<<<ew_grid(n), 256, 0, ST>>>(x, dy, dx, n, accumulate);
+    launch_pdl(silu_bwd_f32_kernel, dim3(ew_grid(n)), dim3(256), size_t(0), ST, x, dy, dx, n, accumulate);
     return launch_checked(int(cudaGetLastError()), "silu_bwd_f32");
 }
 int t2v_silu_bf16(const void* x, void* y, int64_t n, void* stream) {
-    silu_bf16_kernel<<<ew_grid(n), 256, 0, ST>>>(BF(x), BFW(y), n);
+    launch_pdl(silu_bf16_kernel, dim3(ew_grid(n)), dim3(256), size_t(0), ST, BF(x), BFW(y), n);
     return launch_checked(int(cudaGetLastError()), "silu_bf16");
 }
 int t2v_silu_bf16_bwd(const void* x, const void* dy, void* dx, int64_t n, void* stream) {
-    silu_bf16_bwd_kernel<<<ew_grid(n), 256, 0, ST>>>(BF(x), BF(dy), BFW(dx), n);
+    launch_pdl(silu_bf16_bwd_kernel, dim3(ew_grid(n)), dim3(256), size_t(0), ST, BF(x), BF(dy), BFW(dx), n);
     return launch_checked(int(cudaGetLastError()), "silu_bf16_bwd");
 }
 int t2v_add_bf16(const void* a, const void* b, const void* c, void* out, int64_t n, void* stream) {
     if (n % 8) return fail(-2, "add_bf16: n must be a multiple of 8");
-    add_kernel<<<ew_grid(n / 8), 256, 0, ST>>>(BF(a), BF(b), BF(c), BFW(out), n / 8);
+    launch_pdl(add_kernel, dim3(ew_grid(n / 8)), dim3(256), size_t(0), ST, BF(a), BF(b), BF(c), BFW(out), n / 8);
     return launch_checked(int(cudaGetLastError()), "add_bf16");
 }
 int t2v_scale_bf16(const void* a, void* out, int64_t n, float alpha, void* stream) {
     if (n % 8) return fail(-2, "scale_bf16: n must be a multiple of 8");
-    scale_bf16_kernel<<<ew_grid(n / 8), 256, 0, ST>>>(BF(a), BFW(out), n / 8, alpha);
+    launch_pdl(scale_bf16_kernel, dim3(ew_grid(n / 8)), dim3(256), size_t(0), ST, BF(a), BFW(out), n / 8, alpha);
     return launch_checked(int(cudaGetLastError()), "scale_bf16");
 }
 int t2v_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream) {
-    add_f32_kernel<<<ew_grid(n), 256, 0, ST>>>(a, b, out, n);
+    launch_pdl(add_f32_kernel, dim3(ew_grid(n)), dim3(256), size_t(0), ST, a, b, out, n);
     return launch_checked(int(cudaGetLastError()), "add_f32");
 }
 int t2v_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
-    cast_f32_bf16_kernel<<<ew_grid(std::max<int64_t>(n / 8, 1)), 256, 0, ST>>>(src, BFW(dst), n);
+    launch_pdl(cast_f32_bf16_kernel, dim3(ew_grid(std::max<int64_t>(n / 8, 1))), dim3(256), size_t(0), ST, src, BFW(dst), n);
     return launch_checked(int(cudaGetLastError()), "cast_f32_bf16");
 }
 int t2v_upsample_nearest_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t Ho, int32_t Wo, int32_t C, void* stream) {
     if (C % 8) return fail(-2, "upsample: C %% 8 != 0");
-    upsample_nearest_fwd_kernel<<<ew_grid(int64_t(N) * Ho * Wo * (C / 8)), 256, 0, ST>>>(BF(x), BFW(y), N, H, W, Ho, Wo, C);
+    launch_pdl(upsample_nearest_fwd_kernel, dim3(ew_grid(int64_t(N) * Ho * Wo * (C / 8))), dim3(256), size_t(0), ST, BF(x), BFW(y), N, H, W, Ho, Wo, C);
     return launch_checked(int(cudaGetLastError()), "upsample_nearest_fwd");
 }
 int t2v_upsample_nearest_bwd(const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t Ho, int32_t Wo, int32_t C, void* stream) {
     if (C % 8) return fail(-2, "upsample: C %% 8 != 0");
-    upsample_nearest_bwd_kernel<<<ew_grid(int64_t(N) * H * W * (C / 8)), 256, 0, ST>>>(BF(dy), BFW(dx), N, H, W, Ho, Wo, C);
+    launch_pdl(upsample_nearest_bwd_kernel, dim3(ew_grid(int64_t(N) * H * W * (C / 8))), dim3(256), size_t(0), ST, BF(dy), BFW(dx), N, H, W, Ho, Wo, C);
     return launch_checked(int(cudaGetLastError()), "upsample_nearest_bwd");
 }
 int t2v_copy_cols(const void* src, void* dst, int64_t M, int32_t C, int32_t src_ld, int32_t src_off, int32_t dst_ld, int32_t dst_off,
                   void* stream) {
     if (C % 8 || src_ld % 8 || src_off % 8 || dst_ld % 8 || dst_off % 8) return fail(-2, "copy_cols: all extents must be multiples of 8");
-    copy_cols_kernel<<<ew_grid(M * (C / 8)), 256, 0, ST>>>(BF(src), BFW(dst), M, C, src_ld, src_off, dst_ld, dst_off);
+    launch_pdl(copy_cols_kernel, dim3(ew_grid(M * (C / 8))), dim3(256), size_t(0), ST, BF(src), BFW(dst), M, C, src_ld, src_off, dst_ld, dst_off);
     return launch_checked(int(cudaGetLastError()), "copy_cols");
 }
 int t2v_colsum(const void* x, float* out, int32_t S, int64_t P, int32_t C, void* stream) {
@@ -507,38 +530,38 @@ int t2v_colsum(const void* x, float* out, int32_t S, int64_t P, int32_t C, void*
         const int cw = std::min(4096, C - col0);
         int bs = 256;
         while (bs < cw / 8) bs += 32;
-        colsum_kernel<<<dim3(chunks, S), bs, cw * sizeof(float), ST>>>(BF(x), out, P, cw, chunk, C, col0);
+        launch_pdl(colsum_kernel, dim3(dim3(chunks, S)), dim3(bs), size_t(cw * sizeof(float)), ST, BF(x), out, P, cw, chunk, C, col0);
         if (col0) count_launch();
     }
     return launch_checked(int(cudaGetLastError()), "colsum");
 }
 int t2v_colsum_f32(const float* x, float* out, int32_t S, int32_t C, void* stream) {
-    colsum_f32_kernel<<<ew_grid(C), 256, 0, ST>>>(x, out, S, C);
+    launch_pdl(colsum_f32_kernel, dim3(ew_grid(C)), dim3(256), size_t(0), ST, x, out, S, C);
     return launch_checked(int(cudaGetLastError()), "colsum_f32");
 }
 int t2v_softmax_fwd(const float* s, void* p, int64_t rows, int32_t n_valid, int32_t ld_in, int32_t ld_out, void* stream) {
     const int grid = int(std::min<int64_t>((rows + 7) / 8, 148 * 16));
-    softmax_fwd_kernel<<<grid, 256, 0, ST>>>(s, BFW(p), rows, n_valid, ld_in, ld_out);
+    launch_pdl(softmax_fwd_kernel, dim3(grid), dim3(256), size_t(0), ST, s, BFW(p), rows, n_valid, ld_in, ld_out);
     return launch_checked(int(cudaGetLastError()), "softmax_fwd");
 }
 int t2v_softmax_bwd(const void* p, const float* dp, void* ds, int64_t rows, int32_t n_valid, int32_t ld_p, int32_t ld_dp, float scale,
                     void* stream) {
     const int grid = int(std::min<int64_t>((rows + 7) / 8, 148 * 16));
-    softmax_bwd_kernel<<<grid, 256, 0, ST>>>(BF(p), dp, BFW(ds), rows, n_valid, ld_p, ld_dp, scale);
+    launch_pdl(softmax_bwd_kernel, dim3(grid), dim3(256), size_t(0), ST, BF(p), dp, BFW(ds), rows, n_valid, ld_p, ld_dp, scale);
     return launch_checked(int(cudaGetLastError()), "softmax_bwd");
 }
 int t2v_dropout_scale_add(const void* x, const void* base, void* out, int64_t n, float p, float scale, uint64_t seed, void* stream) {
     if (n % 8) return fail(-2, "dropout_scale_add: n must be a multiple of 8");
     if (!(p >= 0.f && p < 1.f)) return fail(-2, "dropout_scale_add: p=%f out of range", p);
-    dropout_scale_add_kernel<<<ew_grid(n / 8), 256, 0, ST>>>(BF(x), BF(base), BFW(out), n / 8, p, scale, seed);
+    launch_pdl(dropout_scale_add_kernel, dim3(ew_grid(n / 8)), dim3(256), size_t(0), ST, BF(x), BF(base), BFW(out), n / 8, p, scale, seed);
     return launch_checked(int(cudaGetLastError()), "dropout_scale_add");
 }
 int t2v_vae_sample(const void* moments, const float* eps, float* out, int32_t B, int32_t F, int32_t HW, float scale, void* stream) {
-    vae_sample_kernel<<<ew_grid(int64_t(B) * F * HW), 256, 0, ST>>>(BF(moments), eps, out, B, F, HW, scale);
+    launch_pdl(vae_sample_kernel, dim3(ew_grid(int64_t(B) * F * HW)), dim3(256), size_t(0), ST, BF(moments), eps, out, B, F, HW, scale);
     return launch_checked(int(cudaGetLastError()), "vae_sample");
 }
 int t2v_timestep_embedding(const int64_t* t, void* out, int32_t B, int32_t dim, void* stream) {
-    timestep_embed_kernel<<<ew_grid(int64_t(B) * dim / 2), 256, 0, ST>>>(t, BFW(out), B, dim);
+    launch_pdl(timestep_embed_kernel, dim3(ew_grid(int64_t(B) * dim / 2)), dim3(256), size_t(0), ST, t, BFW(out), B, dim);
     return launch_checked(int(cudaGetLastError()), "timestep_embedding");
 }
 

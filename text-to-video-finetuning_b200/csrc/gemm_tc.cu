@@ -6,6 +6,7 @@
 //               tcgen05.ld, fused epilogue, smem-staged coalesced global stores / red.add
 //
 // The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
+#include "common.h"
 #include "gemm_tc.cuh"
 #include "ptx.cuh"
 
@@ -281,6 +282,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();  // the prologue above (barriers, TMEM, descriptor prefetch) overlaps the tail of the previous kernel
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -467,8 +469,7 @@ static int launch_impl(const GemmParams& p, cudaStream_t stream) {
     }
     int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
     if (grid < 1) return 0;
-    kern<<<grid, kNumThreads, smem, stream>>>(p);
-    return static_cast<int>(cudaGetLastError());
+    return static_cast<int>(launch_pdl(kern, dim3(grid), dim3(kNumThreads), smem, stream, p));
 }
 
 int launch_gemm(const GemmParams& p, bool a_mn, bool b_mn, cudaStream_t stream) {

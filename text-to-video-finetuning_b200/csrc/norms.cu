@@ -81,6 +81,7 @@ __device__ __forceinline__ void gn_sample_barrier(unsigned* counter, unsigned ta
 
 template <int MODE>
 __global__ void __launch_bounds__(kGnThreads, 1) gn_fused_kernel(const GnArgs g) {
+    pdl_sync();
     extern __shared__ float sh[];  // [2][C] partial sums, then [2][G] group terms
     const int C = g.C, G = g.G, cpg = C / G;
     const int s = blockIdx.x / g.chunks, chunk = blockIdx.x % g.chunks;
@@ -297,6 +298,7 @@ template <int VPL>
 __global__ void ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                               const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ stat,
                               int64_t rows, int C, float eps) {
+    pdl_sync();
     const int V = C >> 3;
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
@@ -353,6 +355,7 @@ __global__ void ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bf
                               const float* __restrict__ gamma, const float* __restrict__ stat,
                               const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ dx,
                               float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int C) {
+    pdl_sync();
     const int V = C >> 3;
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
@@ -469,7 +472,7 @@ static int gn_launch(GnArgs& g, void* workspace, int S, cudaStream_t st) {
     g.accum = static_cast<float*>(workspace);
     g.arrive = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + ab);
     cudaMemsetAsync(workspace, 0, ab + size_t(S) * sizeof(unsigned), st);
-    gn_fused_kernel<MODE><<<S * g.chunks, kGnThreads, std::max<size_t>(2 * g.C, 2 * g.G) * sizeof(float), st>>>(g);
+    launch_pdl(gn_fused_kernel<MODE>, dim3(S * g.chunks), dim3(kGnThreads), std::max<size_t>(2 * g.C, 2 * g.G) * sizeof(float), st, g);
     count_launch(1);
     return 0;
 }
@@ -511,16 +514,16 @@ int t2v_groupnorm_bwd(const void* dy, const void* x, const float* gamma, const f
     return launch_checked(int(cudaGetLastError()), "groupnorm_bwd");
 }
 
-#define LN_DISPATCH(KERNEL, ...)                                                       \
-    switch (vpl) {                                                                     \
-        case 1: KERNEL<1> __VA_ARGS__; break;                                          \
-        case 2: KERNEL<2> __VA_ARGS__; break;                                          \
-        case 3: KERNEL<3> __VA_ARGS__; break;                                          \
-        case 4: KERNEL<4> __VA_ARGS__; break;                                          \
-        case 5: KERNEL<5> __VA_ARGS__; break;                                          \
-        case 6: KERNEL<6> __VA_ARGS__; break;                                          \
-        case 7: KERNEL<7> __VA_ARGS__; break;                                          \
-        default: KERNEL<8> __VA_ARGS__; break;                                         \
+#define LN_DISPATCH(KERNEL, GRID, SMEM, ST, ...)                                                       \
+    switch (vpl) {                                                                                         \
+        case 1: launch_pdl(KERNEL<1>, dim3(GRID), dim3(256), size_t(SMEM), ST, __VA_ARGS__); break;       \
+        case 2: launch_pdl(KERNEL<2>, dim3(GRID), dim3(256), size_t(SMEM), ST, __VA_ARGS__); break;       \
+        case 3: launch_pdl(KERNEL<3>, dim3(GRID), dim3(256), size_t(SMEM), ST, __VA_ARGS__); break;       \
+        case 4: launch_pdl(KERNEL<4>, dim3(GRID), dim3(256), size_t(SMEM), ST, __VA_ARGS__); break;       \
+        case 5: launch_pdl(KERNEL<5>, dim3(GRID), dim3(256), size_t(SMEM), ST, __VA_ARGS__); break;       \
+        case 6: launch_pdl(KERNEL<6>, dim3(GRID), dim3(256), size_t(SMEM), ST, __VA_ARGS__); break;       \
+        case 7: launch_pdl(KERNEL<7>, dim3(GRID), dim3(256), size_t(SMEM), ST, __VA_ARGS__); break;       \
+        default: launch_pdl(KERNEL<8>, dim3(GRID), dim3(256), size_t(SMEM), ST, __VA_ARGS__); break;      \
     }
 
 int t2v_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stat, int64_t rows, int32_t C,
@@ -529,8 +532,8 @@ int t2v_layernorm_fwd(const void* x, const float* gamma, const float* beta, void
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     const int vpl = (C / 8 + 31) / 32;
     const int grid = int(std::min<int64_t>((rows + 7) / 8, 148 * 8));
-    LN_DISPATCH(ln_fwd_kernel, <<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), gamma, beta,
-                                                     static_cast<__nv_bfloat16*>(y), stat, rows, C, eps));
+    LN_DISPATCH(ln_fwd_kernel, grid, 0, st, static_cast<const __nv_bfloat16*>(x), gamma, beta, static_cast<__nv_bfloat16*>(y), stat,
+                rows, C, eps);
     return launch_checked(int(cudaGetLastError()), "layernorm_fwd");
 }
 
@@ -540,9 +543,9 @@ int t2v_layernorm_bwd(const void* dy, const void* x, const float* gamma, const f
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     const int vpl = (C / 8 + 31) / 32;
     const int grid = int(std::min<int64_t>((rows + 7) / 8, 148 * 2));
-    LN_DISPATCH(ln_bwd_kernel, <<<grid, 256, 2 * C * sizeof(float), st>>>(
-                    static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), gamma, stat,
-                    static_cast<const __nv_bfloat16*>(add), static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, rows, C));
+    LN_DISPATCH(ln_bwd_kernel, grid, 2 * C * sizeof(float), st, static_cast<const __nv_bfloat16*>(x),
+                static_cast<const __nv_bfloat16*>(dy), gamma, stat, static_cast<const __nv_bfloat16*>(add),
+                static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, rows, C);
     return launch_checked(int(cudaGetLastError()), "layernorm_bwd");
 }
 
