@@ -46,6 +46,9 @@ typedef struct {
     int32_t out_fp32;       /* 0: bf16 output, 1: fp32 output                                             */
     int32_t rowbias_div;    /* rowbias row = n / rowbias_div (frames per clip: one time-embedding row per
                                clip instead of the reference's repeat_interleave, unet_3d_condition.py:400) */
+    void* workspace;        /* optional scratch of t2v_conv_workspace_bytes(...) bytes: lets conv_fwd / conv_dgrad
+                               split the reduction over SMs when the output has few tiles (deep, small maps)   */
+    int64_t workspace_bytes;
 } T2VEpilogue;
 
 /* Implicit-GEMM convolution forward on tcgen05 tensor cores (TMA-fed, zero padding by TMA OOB fill).
@@ -65,6 +68,11 @@ int t2v_conv_fwd(const void* x, const void* w, void* y, int32_t N, int32_t H, in
 int t2v_conv_dgrad(const void* dy, const void* w, void* dx, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
                    int32_t KH, int32_t KW, int32_t stride, int32_t pad_h0, int32_t pad_h1, int32_t pad_w0,
                    int32_t pad_w1, const T2VEpilogue* epi, void* stream);
+
+/* Scratch bytes t2v_conv_fwd (dgrad = 0) / t2v_conv_dgrad (dgrad = 1) would like for this problem (0: none).
+ * Without the scratch the same result is computed unsplit (slower on the 4x4 .. 16x16 levels of the UNet).   */
+int64_t t2v_conv_workspace_bytes(int32_t dgrad, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t KH, int32_t KW,
+                                 int32_t stride, int32_t pad_h0, int32_t pad_h1, int32_t pad_w0, int32_t pad_w1);
 
 /* Weight gradient: dw [Cout][KH][KW][Cin] (fp32) += dy^T * shifted(x).  Split over pixels to fill the GPU;
  * partial products are reduced with red.global.add.f32 directly into the fp32 gradient buffer.              */

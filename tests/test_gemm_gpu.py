@@ -111,6 +111,56 @@ def test_conv_dgrad_wgrad(case):
     assert e < 2e-3, f"wgrad rel err {e}"
 
 
+SPLITK_CASES = [
+    (16, 4, 4, 640, 640, 3, 3, 1, (1, 1, 1, 1)),        # deepest resnet conv: 2 x 4 output tiles, 90 k-blocks
+    (1, 16, 16, 1280, 1280, 3, 1, 1, (1, 1, 0, 0)),     # temporal conv at 4x4: W=H*W, H=F
+    (4, 8, 8, 512, 256, 3, 3, 1, (1, 1, 1, 1)),
+    (1, 1, 256, 5120, 1280, 1, 1, 1, (0, 0, 0, 0)),     # FeedForward out-projection on a small map
+]
+
+
+@pytest.mark.parametrize("case", SPLITK_CASES)
+def test_conv_splitk_scratch(case):
+    """Few-tile problems split their reduction over the SMs when the caller passes the scratch the planner asks for."""
+    nat = _lib()
+    N, H, W, Ci, Co, KH, KW, s, pads = case
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(N, H, W, Ci, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Co, KH, KW, Ci, device="cuda", generator=g) / (KH * KW * Ci) ** 0.5).bfloat16()
+    bias = torch.randn(Co, device="cuda", generator=g)
+    rowbias = torch.randn((N + 1) // 2, Co, device="cuda", generator=g)
+    ref = conv_ref(x, w, s, pads)
+    Ho, Wo = ref.shape[1], ref.shape[2]
+    res = torch.randn(N, Ho, Wo, Co, device="cuda", generator=g).bfloat16()
+    nbytes = nat.lib().t2v_conv_workspace_bytes(0, N, H, W, Ci, Co, KH, KW, s, *pads)
+    assert nbytes == N * Ho * Wo * Co * 4, "planner should ask for split-K scratch on this shape"
+    ws = torch.full((nbytes // 4,), float("nan"), device="cuda")
+    rb_div = 2 if N > 1 else 1
+    ref2 = 0.5 * ref + bias + rowbias[torch.arange(N, device="cuda") // rb_div][:, None, None, :] + res.float()
+    for out_fp32, tol in ((0, 1e-2), (1, 2e-3)):
+        y = torch.full((N, Ho, Wo, Co), float("nan"), device="cuda", dtype=torch.float32 if out_fp32 else torch.bfloat16)
+        epi = nat.Epilogue(bias.data_ptr(), rowbias.data_ptr(), res.data_ptr(), 0.5, out_fp32, rb_div, ws.data_ptr(), nbytes)
+        nat.check(nat.lib().t2v_conv_fwd(P(x), P(w), P(y), N, H, W, Ci, Co, KH, KW, s, *pads, ctypes.byref(epi), stream()))
+        torch.cuda.synchronize()
+        e = rel_err(y, ref2)
+        assert e < tol, f"split-K conv fwd rel err {e}"
+    # dgrad with residual
+    dy = torch.randn(N, Ho, Wo, Co, device="cuda", generator=g).bfloat16()
+    xf = x.float().requires_grad_(True)
+    ph0, ph1, pw0, pw1 = pads
+    F.conv2d(F.pad(xf.permute(0, 3, 1, 2), (pw0, pw1, ph0, ph1)), w.float().permute(0, 3, 1, 2), stride=s).permute(0, 2, 3, 1).backward(dy.float())
+    other = torch.randn(N, H, W, Ci, device="cuda", generator=g).bfloat16()
+    nb = nat.lib().t2v_conv_workspace_bytes(1, N, H, W, Ci, Co, KH, KW, s, *pads)
+    assert nb in (0, N * H * W * Ci * 4)   # the data gradient of a wide projection has enough tiles without splitting
+    ws = torch.full((max(nb, 4) // 4,), float("nan"), device="cuda")
+    dx = torch.full((N, H, W, Ci), float("nan"), device="cuda", dtype=torch.bfloat16)
+    epi = nat.Epilogue(None, None, other.data_ptr(), 1.0, 0, 1, ws.data_ptr() if nb else None, nb)
+    nat.check(nat.lib().t2v_conv_dgrad(P(dy), P(w), P(dx), N, H, W, Ci, Co, KH, KW, s, *pads, ctypes.byref(epi), stream()))
+    torch.cuda.synchronize()
+    e = rel_err(dx, xf.grad + other.float())
+    assert e < 1e-2, f"split-K dgrad rel err {e}"
+
+
 BGEMM_CASES = [
     # M, N, K, Z1, Z2, a_kmajor, b_kmajor, out_mode
     (1024, 1024, 64, 2, 5, 1, 1, 1),   # S = Q K^T per (frame, head), fp32

@@ -3,9 +3,12 @@
 #include "common.h"
 #include "gemm_tc.cuh"
 
+#include "ptx.cuh"
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <cuda_bf16.h>
 
 using namespace t2v;
 
@@ -51,7 +54,10 @@ struct Tiling {
 // (2*bn clk per 64-deep k-block and 128-row half), so wide tiles and 256-row tiles (B shared by two accumulators) win
 // whenever enough tiles remain to fill the 148 SMs.
 //   row_dims[0..2] = tile counts of tile variables 1..3 (unpaired), extra = product of the remaining tile variables.
-Tiling choose_tiling(const int row_dims[3], int ncols, bool mn_major_b, int kblocks, int64_t extra, bool allow_pair) {
+//   splits_out != nullptr: the reduction may also be split over `s` CTAs per tile (fp32 red.add into scratch + a finishing
+//   pass, see launch_split) - chosen jointly, otherwise few-tile problems would be pushed to tiny, operand-hungry tiles.
+Tiling choose_tiling(const int row_dims[3], int ncols, bool mn_major_b, int kblocks, int64_t extra, bool allow_pair,
+                     int* splits_out = nullptr) {
     const int sms = device_sm_count();
     const int forced_bn = env_int("T2V_FORCE_BN"), forced_mh = env_int("T2V_FORCE_MH");
     Tiling best{16, 1, -1};
@@ -81,18 +87,27 @@ Tiling choose_tiling(const int row_dims[3], int ncols, bool mn_major_b, int kblo
             const int stage_bytes = mh * kBlockM * 128 + b_bytes;
             const int budget = 232448 - 1024 - 256 - kEpilogueStagingBytes;
             if (budget / stage_bytes < 3) continue;
-            const int64_t tiles = m_tiles * ((ncols + bn - 1) / bn) * extra;
-            const int64_t waves = (tiles + sms - 1) / sms;
-            const double active = double(std::min<int64_t>(tiles, sms));
-            // three ceilings per k-block: tcgen05 issue rate, chip-wide L2->SM bandwidth shared by the active CTAs, and
-            // the per-SM shared-memory fill rate (~48 B/clk measured)
-            const double t_kb = std::max({double(mh) * 2.0 * bn, stage_bytes * active / 5200.0, stage_bytes / 48.0, 260.0});
-            const bool overlap = mh == 1 || bn <= 128;  // two TMEM accumulator stages available
-            const double t_epi = (bn / 32.0 + 1.0) * 450.0 * (mh == 2 ? 1.0 : 0.5) * (overlap ? 0.35 : 1.0);
-            const double cost = double(waves) * (kblocks * t_kb + t_epi + 1800.0);
-            if (cost < best_cost - 1e-9) {
-                best_cost = cost;
-                best = Tiling{bn, mh, pv};
+            const int64_t base_tiles = m_tiles * ((ncols + bn - 1) / bn) * extra;
+            const int max_s = (splits_out && base_tiles * 2 <= sms && kblocks >= 8) ? std::min(kblocks / 4, 64) : 1;
+            for (int s = 1; s <= max_s; ++s) {
+                const int kper = (kblocks + s - 1) / s;
+                if ((kblocks + kper - 1) / kper != s) continue;  // same schedule as a smaller s
+                const int64_t tiles = base_tiles * s;
+                const int64_t waves = (tiles + sms - 1) / sms;
+                const double active = double(std::min<int64_t>(tiles, sms));
+                // three ceilings per k-block: tcgen05 issue rate, chip-wide L2->SM bandwidth shared by the active CTAs,
+                // and the per-SM shared-memory fill rate (~48 B/clk measured)
+                const double t_kb = std::max({double(mh) * 2.0 * bn, stage_bytes * active / 5200.0, stage_bytes / 48.0, 260.0});
+                const bool overlap = mh == 1 || bn <= 128;  // two TMEM accumulator stages available
+                const double t_epi = (bn / 32.0 + 1.0) * 450.0 * (mh == 2 ? 1.0 : 0.5) * (overlap ? 0.35 : 1.0);
+                double cost = double(waves) * (kper * t_kb + t_epi + 1800.0);
+                // split: red.add traffic (~2500 B/clk chip-wide) + the memset and finishing launches
+                if (s > 1) cost += double(tiles) * mh * kBlockM * bn * 4.0 / 2500.0 + 10000.0;
+                if (cost < best_cost - 1e-9) {
+                    best_cost = cost;
+                    best = Tiling{bn, mh, pv};
+                    if (splits_out) *splits_out = s;
+                }
             }
         }
     }
@@ -186,13 +201,79 @@ int check_channels(int c, const char* what) {
     return 0;
 }
 
+
+// ---- split-K for forward / data-gradient problems with few output tiles (the 4x4 / 8x8 / 16x16 levels of the UNet:
+// 16-40 tiles of up to 180 k-blocks each would leave most of the 148 SMs idle).  The k-range is split over tile variable
+// 4, partial tiles are reduced with red.global.add.f32 into an fp32 scratch image of the output, and one elementwise
+// kernel applies alpha / bias / row bias / residual and writes the bf16 (or fp32) result.
+void apply_fwd_splits(GemmParams& p, int splits, int kb_total) {
+    p.kb_per_split = (kb_total + splits - 1) / splits;
+    p.tdim[4] = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
+    p.ksplit_var = 4;
+}
+
+__global__ void splitk_finish_kernel(const float* __restrict__ acc, const float* __restrict__ bias, const float* __restrict__ rowbias,
+                                     const __nv_bfloat16* __restrict__ residual, void* __restrict__ out, int64_t rows, int C,
+                                     int64_t rows_per_sample, int rb_div, int64_t rb_ld, float alpha, int out_fp32) {
+    pdl_sync();
+    const int V = C >> 2;  // 4 columns per thread
+    const int64_t total = rows * V;
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t r = i / V;
+        const int c = int(i % V) * 4;
+        float4 v = __ldcg(reinterpret_cast<const float4*>(acc + r * C + c));
+        v.x *= alpha; v.y *= alpha; v.z *= alpha; v.w *= alpha;
+        if (bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c));
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        }
+        if (rowbias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(rowbias + (r / rows_per_sample / rb_div) * rb_ld + c));
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        }
+        if (residual) {
+            const uint2 q = __ldg(reinterpret_cast<const uint2*>(residual + r * C + c));
+            v.x += bf16_lo(q.x); v.y += bf16_hi(q.x); v.z += bf16_lo(q.y); v.w += bf16_hi(q.y);
+        }
+        if (out_fp32) {
+            reinterpret_cast<float4*>(static_cast<float*>(out) + r * C)[c >> 2] = v;
+        } else {
+            uint2 q;
+            q.x = pack_bf16(v.x, v.y);
+            q.y = pack_bf16(v.z, v.w);
+            reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out) + r * C)[c >> 2] = q;
+        }
+    }
+}
+
+// Runs the planned problem split over k into `ws` and finishes into the real output.  `e` is the caller's epilogue.
+int launch_split(GemmParams& p, bool a_mn, bool b_mn, const T2VEpilogue& e, void* out, int64_t rows, int C, int64_t rows_per_sample,
+                 cudaStream_t st, const char* what) {
+    const size_t bytes = size_t(rows) * C * sizeof(float);
+    if (!e.workspace || size_t(e.workspace_bytes) < bytes) return fail(-3, "%s: split-K needs %zu bytes of workspace", what, bytes);
+    cudaMemsetAsync(e.workspace, 0, bytes, st);
+    p.out = e.workspace;
+    p.out_mode = OUT_F32_RED;
+    p.alpha = 1.0f;
+    p.bias = nullptr; p.rowbias = nullptr; p.residual = nullptr;
+    p.flags = 0;
+    set_vec_flag(p);
+    if (int r = launch_checked(launch_gemm(p, a_mn, b_mn, st), what)) return r;
+    const int64_t vec = rows * (C / 4);
+    const int grid = int(std::min<int64_t>((vec + 255) / 256, 148 * 8));
+    const int rc = int(launch_pdl(splitk_finish_kernel, dim3(grid), dim3(256), 0, st, static_cast<const float*>(e.workspace), e.bias,
+                                  e.rowbias, static_cast<const __nv_bfloat16*>(e.residual), out, rows, C, rows_per_sample,
+                                  e.rowbias_div > 0 ? e.rowbias_div : 1, int64_t(C), e.alpha, e.out_fp32));
+    return launch_checked(rc, what);
+}
+
 }  // namespace
 
 extern "C" {
 
-int t2v_conv_fwd(const void* x, const void* w, void* y, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
-                 int32_t KH, int32_t KW, int32_t stride, int32_t pad_h0, int32_t pad_h1, int32_t pad_w0, int32_t pad_w1,
-                 const T2VEpilogue* epi, void* stream) {
+static int conv_fwd_impl(const void* x, const void* w, void* y, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                         int32_t KH, int32_t KW, int32_t stride, int32_t pad_h0, int32_t pad_h1, int32_t pad_w0, int32_t pad_w1,
+                         const T2VEpilogue* epi, void* stream, bool plan_only) {
     if (int r = check_channels(Cin, "Cin")) return r;
     if (Cout <= 0 || N <= 0 || H <= 0 || W <= 0) return fail(-2, "conv_fwd: bad shape");
     if (stride != 1 && stride != 2) return fail(-2, "conv_fwd: stride %d unsupported", stride);
@@ -209,10 +290,13 @@ int t2v_conv_fwd(const void* x, const void* w, void* y, int32_t N, int32_t H, in
     p.kdim[1] = KW;
     p.kdim[2] = KH;
     p.ksplit_var = -1;
+    int splits = 1;
     {
         const int rd[3] = {p.tdim[1], p.tdim[2], p.tdim[3]};
-        apply_tiling(p, choose_tiling(rd, Cout, false, p.kdim[0] * KW * KH, 1, true));
+        const bool may_split = (plan_only || (epi && epi->workspace)) && Cout % 8 == 0 && !env_int("T2V_NO_SPLIT");
+        apply_tiling(p, choose_tiling(rd, Cout, false, p.kdim[0] * KW * KH, 1, true, may_split ? &splits : nullptr));
     }
+    if (plan_only) return splits;
     p.tdim[0] = (Cout + p.block_n - 1) / p.block_n;
     // A: activations, K-major pixel box with tap shifts
     {
@@ -221,7 +305,8 @@ int t2v_conv_fwd(const void* x, const void* w, void* y, int32_t N, int32_t H, in
         const uint64_t str[3] = {uint64_t(Cin) * 2, uint64_t(W) * Cin * 2, uint64_t(H) * W * Cin * 2};
         const uint32_t box[4] = {64, uint32_t(bx.w * stride), uint32_t(bx.h * stride), uint32_t(bx.n)};
         const uint32_t est[4] = {1, uint32_t(stride), uint32_t(stride), 1};
-        if (int r = encode_tmap_bf16(&a.map, x, 4, dims, str, box, est)) return fail(r, "conv_fwd: A tensor map (%d)", r);
+        if (!plan_only)
+            if (int r = encode_tmap_bf16(&a.map, x, 4, dims, str, box, est)) return fail(r, "conv_fwd: A tensor map (%d)", r);
         a.rank = 4; a.nbox = 1; a.box_dim = 0; a.box_step = 0; a.box_bytes = bx.w * bx.h * bx.n * 128;
         a.base[1] = -pad_w0; a.base[2] = -pad_h0;
         a.tcoef[1][1] = bx.w * stride; a.tcoef[2][2] = bx.h * stride; a.tcoef[3][3] = bx.n;
@@ -234,7 +319,8 @@ int t2v_conv_fwd(const void* x, const void* w, void* y, int32_t N, int32_t H, in
         const uint64_t dims[2] = {kt, uint64_t(Cout)};
         const uint64_t str[1] = {kt * 2};
         const uint32_t box[2] = {64, uint32_t(p.block_n)};
-        if (int r = encode_tmap_bf16(&b.map, w, 2, dims, str, box, nullptr)) return fail(r, "conv_fwd: B tensor map (%d)", r);
+        if (!plan_only)
+            if (int r = encode_tmap_bf16(&b.map, w, 2, dims, str, box, nullptr)) return fail(r, "conv_fwd: B tensor map (%d)", r);
         b.rank = 2; b.nbox = 1; b.box_bytes = p.block_n * 128;
         b.tcoef[1][0] = p.block_n;
         b.kcoef[0][0] = kBlockK; b.kcoef[0][1] = Cin; b.kcoef[0][2] = KW * Cin;
@@ -245,13 +331,19 @@ int t2v_conv_fwd(const void* x, const void* w, void* y, int32_t N, int32_t H, in
     p.ldw = Cout; p.ldh = int64_t(Wo) * Cout; p.ldn = int64_t(Ho) * Wo * Cout;
     p.rb_ld = Cout;
     fill_epilogue(p, epi, y, OUT_BF16);
+    const int kb_total = p.kdim[0] * p.kdim[1] * p.kdim[2];
+    if (splits > 1) {
+        apply_fwd_splits(p, splits, kb_total);
+        finish_common(p, false);
+        return launch_split(p, false, false, *epi, y, int64_t(N) * Ho * Wo, Cout, int64_t(Ho) * Wo, static_cast<cudaStream_t>(stream), "conv_fwd");
+    }
     set_vec_flag(p);
     return launch_checked(launch_gemm(p, false, false, static_cast<cudaStream_t>(stream)), "conv_fwd");
 }
 
-int t2v_conv_dgrad(const void* dy, const void* w, void* dx, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
-                   int32_t KH, int32_t KW, int32_t stride, int32_t pad_h0, int32_t pad_h1, int32_t pad_w0,
-                   int32_t pad_w1, const T2VEpilogue* epi, void* stream) {
+static int conv_dgrad_impl(const void* dy, const void* w, void* dx, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                           int32_t KH, int32_t KW, int32_t stride, int32_t pad_h0, int32_t pad_h1, int32_t pad_w0,
+                           int32_t pad_w1, const T2VEpilogue* epi, void* stream, bool plan_only) {
     if (int r = check_channels(Cin, "Cin")) return r;
     if (int r = check_channels(Cout, "Cout")) return r;
     if (stride != 1 && stride != 2) return fail(-2, "conv_dgrad: stride %d unsupported", stride);
@@ -276,17 +368,22 @@ int t2v_conv_dgrad(const void* dy, const void* w, void* dx, int32_t N, int32_t H
             p.kdim[1] = ntw;
             p.kdim[2] = nth;
             p.ksplit_var = -1;
+            int splits = 1;
             {
                 const int rd[3] = {p.tdim[1], p.tdim[2], p.tdim[3]};
-                apply_tiling(p, choose_tiling(rd, Cin, true, p.kdim[0] * ntw * nth, 1, true));
+                // split-K only for the single-class (stride 1) problem: the scratch image is the whole dx
+                const bool may_split = s == 1 && (plan_only || (epi && epi->workspace)) && !env_int("T2V_NO_SPLIT");
+                apply_tiling(p, choose_tiling(rd, Cin, true, p.kdim[0] * ntw * nth, 1, true, may_split ? &splits : nullptr));
             }
+            if (plan_only) return splits;
             p.tdim[0] = (Cin + p.block_n - 1) / p.block_n;
             {
                 TmaOperand& a = p.a;  // dy, K-major (K = Cout), pixel box shifted against the tap
                 const uint64_t dims[4] = {uint64_t(Cout), uint64_t(Wo), uint64_t(Ho), uint64_t(N)};
                 const uint64_t str[3] = {uint64_t(Cout) * 2, uint64_t(Wo) * Cout * 2, uint64_t(Ho) * Wo * Cout * 2};
                 const uint32_t box[4] = {64, uint32_t(bx.w), uint32_t(bx.h), uint32_t(bx.n)};
-                if (int r = encode_tmap_bf16(&a.map, dy, 4, dims, str, box, nullptr)) return fail(r, "conv_dgrad: A tensor map (%d)", r);
+                if (!plan_only)
+                    if (int r = encode_tmap_bf16(&a.map, dy, 4, dims, str, box, nullptr)) return fail(r, "conv_dgrad: A tensor map (%d)", r);
                 a.rank = 4; a.nbox = 1; a.box_bytes = bx.w * bx.h * bx.n * 128;
                 a.base[1] = (pw + pad_w0 - tw0) / s; a.base[2] = (ph + pad_h0 - th0) / s;
                 a.tcoef[1][1] = bx.w; a.tcoef[2][2] = bx.h; a.tcoef[3][3] = bx.n;
@@ -297,7 +394,8 @@ int t2v_conv_dgrad(const void* dy, const void* w, void* dx, int32_t N, int32_t H
                 const uint64_t dims[3] = {uint64_t(Cin), uint64_t(KH) * KW, uint64_t(Cout)};
                 const uint64_t str[2] = {uint64_t(Cin) * 2, uint64_t(KH) * KW * Cin * 2};
                 const uint32_t box[3] = {64, 1, 64};
-                if (int r = encode_tmap_bf16(&b.map, w, 3, dims, str, box, nullptr)) return fail(r, "conv_dgrad: B tensor map (%d)", r);
+                if (!plan_only)
+                    if (int r = encode_tmap_bf16(&b.map, w, 3, dims, str, box, nullptr)) return fail(r, "conv_dgrad: B tensor map (%d)", r);
                 b.rank = 3; b.nbox = (p.block_n + 63) / 64; b.box_dim = 0; b.box_step = 64; b.box_bytes = 8192;
                 b.base[1] = th0 * KW + tw0;
                 b.tcoef[0][0] = p.block_n;
@@ -309,15 +407,46 @@ int t2v_conv_dgrad(const void* dy, const void* w, void* dx, int32_t N, int32_t H
             p.ldw = int64_t(s) * Cin; p.ldh = int64_t(s) * W * Cin; p.ldn = int64_t(H) * W * Cin;
             p.rb_ld = Cin;
             const int64_t base_off = (int64_t(ph) * W + pw) * Cin;
-            T2VEpilogue e = epi ? *epi : T2VEpilogue{nullptr, nullptr, nullptr, 1.0f, 0, 1};
+            T2VEpilogue e = epi ? *epi : T2VEpilogue{nullptr, nullptr, nullptr, 1.0f, 0, 1, nullptr, 0};
             const size_t esz = e.out_fp32 ? 4 : 2;
             fill_epilogue(p, &e, static_cast<char*>(dx) + base_off * esz, OUT_BF16);
             if (p.residual) p.residual = static_cast<const char*>(p.residual) + base_off * 2;
+            if (splits > 1) {
+                apply_fwd_splits(p, splits, p.kdim[0] * p.kdim[1] * p.kdim[2]);
+                finish_common(p, true);
+                return launch_split(p, false, true, e, dx, int64_t(N) * H * W, Cin, int64_t(H) * W, static_cast<cudaStream_t>(stream), "conv_dgrad");
+            }
             set_vec_flag(p);
             if (int r = launch_checked(launch_gemm(p, false, true, static_cast<cudaStream_t>(stream)), "conv_dgrad")) return r;
         }
     }
     return 0;
+}
+
+int t2v_conv_fwd(const void* x, const void* w, void* y, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                 int32_t KH, int32_t KW, int32_t stride, int32_t pad_h0, int32_t pad_h1, int32_t pad_w0, int32_t pad_w1,
+                 const T2VEpilogue* epi, void* stream) {
+    return conv_fwd_impl(x, w, y, N, H, W, Cin, Cout, KH, KW, stride, pad_h0, pad_h1, pad_w0, pad_w1, epi, stream, false);
+}
+
+int t2v_conv_dgrad(const void* dy, const void* w, void* dx, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                   int32_t KH, int32_t KW, int32_t stride, int32_t pad_h0, int32_t pad_h1, int32_t pad_w0,
+                   int32_t pad_w1, const T2VEpilogue* epi, void* stream) {
+    return conv_dgrad_impl(dy, w, dx, N, H, W, Cin, Cout, KH, KW, stride, pad_h0, pad_h1, pad_w0, pad_w1, epi, stream, false);
+}
+
+int64_t t2v_conv_workspace_bytes(int32_t dgrad, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t KH, int32_t KW,
+                                 int32_t stride, int32_t pad_h0, int32_t pad_h1, int32_t pad_w0, int32_t pad_w1) {
+    if (Cin <= 0 || Cout <= 0 || Cin % 8 || Cout % 8 || (stride != 1 && stride != 2)) return 0;
+    if (dgrad) {
+        const int splits = conv_dgrad_impl(nullptr, nullptr, nullptr, N, H, W, Cin, Cout, KH, KW, stride, pad_h0, pad_h1, pad_w0, pad_w1,
+                                           nullptr, nullptr, true);
+        return splits > 1 ? int64_t(N) * H * W * Cin * 4 : 0;
+    }
+    const int Ho = (H + pad_h0 + pad_h1 - KH) / stride + 1, Wo = (W + pad_w0 + pad_w1 - KW) / stride + 1;
+    const int splits = conv_fwd_impl(nullptr, nullptr, nullptr, N, H, W, Cin, Cout, KH, KW, stride, pad_h0, pad_h1, pad_w0, pad_w1,
+                                     nullptr, nullptr, true);
+    return splits > 1 ? int64_t(N) * Ho * Wo * Cout * 4 : 0;
 }
 
 int t2v_conv_wgrad(const void* x, const void* dy, float* dw, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,

@@ -39,6 +39,14 @@ def out_hw(H, W, KH, KW, stride, pads):
 
 
 # ---------------------------------------------------------------------------------------------- tensor-core family
+def _conv_scratch(dgrad, N, H, W, Ci, Co, KH, KW, stride, pads, device):
+    """fp32 scratch the planner asks for when it wants to split the reduction of a few-tile problem over the SMs."""
+    n = native.lib().t2v_conv_workspace_bytes(dgrad, N, H, W, Ci, Co, KH, KW, stride, *pads)
+    if n <= 0:
+        return None, 0
+    return torch.empty(n // 4, device=device, dtype=torch.float32), n
+
+
 def conv_fwd(x, w, bias=None, rowbias=None, residual=None, stride=1, pads=(0, 0, 0, 0), alpha=1.0, out_fp32=False, rowbias_div=1):
     """x [N,H,W,Ci] bf16, w [Co,KH,KW,Ci] bf16 -> y [N,Ho,Wo,Co]; y = alpha*conv + bias[c] + rowbias[n,c] + residual."""
     _chk_bf16(x, w, residual)
@@ -48,8 +56,10 @@ def conv_fwd(x, w, bias=None, rowbias=None, residual=None, stride=1, pads=(0, 0,
     assert Ci == Ci2, (x.shape, w.shape)
     Ho, Wo = out_hw(H, W, KH, KW, stride, pads)
     y = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    ws, ws_bytes = _conv_scratch(0, N, H, W, Ci, Co, KH, KW, stride, pads, x.device)
     epi = native.Epilogue(bias.data_ptr() if bias is not None else None, rowbias.data_ptr() if rowbias is not None else None,
-                          residual.data_ptr() if residual is not None else None, float(alpha), int(out_fp32), int(rowbias_div))
+                          residual.data_ptr() if residual is not None else None, float(alpha), int(out_fp32), int(rowbias_div),
+                          ws.data_ptr() if ws is not None else None, ws_bytes)
     native.check(native.lib().t2v_conv_fwd(_p(x), _p(w), _p(y), N, H, W, Ci, Co, KH, KW, stride, *pads, ctypes.byref(epi), _stream()))
     return y
 
@@ -61,7 +71,9 @@ def conv_dgrad(dy, w, in_hw, stride=1, pads=(0, 0, 0, 0), residual=None):
     H, W = in_hw
     Co, KH, KW, Ci = w.shape
     dx = torch.empty((N, H, W, Ci), device=dy.device, dtype=torch.bfloat16)
-    epi = native.Epilogue(None, None, residual.data_ptr() if residual is not None else None, 1.0, 0, 1)
+    ws, ws_bytes = _conv_scratch(1, N, H, W, Ci, Co, KH, KW, stride, pads, dy.device)
+    epi = native.Epilogue(None, None, residual.data_ptr() if residual is not None else None, 1.0, 0, 1,
+                          ws.data_ptr() if ws is not None else None, ws_bytes)
     native.check(native.lib().t2v_conv_dgrad(_p(dy), _p(w), _p(dx), N, H, W, Ci, Co, KH, KW, stride, *pads, ctypes.byref(epi), _stream()))
     return dx
 
