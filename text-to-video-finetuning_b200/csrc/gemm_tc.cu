@@ -124,12 +124,12 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
         mbar_wait(&acc_full[as], aphase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + as * p.acc_stage_cols + (p.mh == 2 ? grp * p.acc_half_cols : 0u);
-        for (int ch = c_begin; ch < c_end; ++ch) {
+        uint32_t acc[32];
+        if (c_begin < c_end) tmem_ld32(taddr + c_begin * 32, acc);  // software pipeline: chunk ch+1 is read from TMEM while
+        for (int ch = c_begin; ch < c_end; ++ch) {                  // chunk ch goes through staging and out to global memory
             const int32_t col = col0 + ch * 32;
             const int32_t cvalid = min(32, min(p.block_n - ch * 32, p.ncols - col));  // valid columns of this chunk
             __syncwarp();
-            uint32_t acc[32];
-            tmem_ld32(taddr + ch * 32, acc);            // issue the TMEM read first; global loads below overlap with it
             float bval = 0.f;
             if (has_bias && static_cast<int32_t>(lane) < cvalid) bval = __ldg(p.bias + col + lane);
             if (vec && has_res && cvalid > 0) {         // residual: coalesced global -> staging (bf16, 4 chunks per row)
@@ -146,11 +146,12 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
             }
             sbias[lane] = bval;
             tmem_ld_wait();
-            __syncwarp();
-            if (cvalid <= 0) continue;
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * p.alpha;
+            if (ch + 1 < c_end) tmem_ld32(taddr + (ch + 1) * 32, acc);
+            __syncwarp();
+            if (cvalid <= 0) continue;
             if (vec) {
                 if (has_bias) {
 #pragma unroll
@@ -215,22 +216,27 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
                                           __uint_as_float(q.w));
                         }
                     } else {  // ragged last chunk: element-wise
+                        // (static indexing only: a runtime-indexed register array would be demoted to local memory)
                         const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
-                        for (int e = 0; e < nval; ++e) {
+#pragma unroll
+                        for (int e = 0; e < EPC; ++e) {
+                            if (e >= nval) break;
                             if (ESZ == 2) {
                                 const uint32_t h = (w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
                                 reinterpret_cast<uint16_t*>(p.out)[o + e] = static_cast<uint16_t>(h);
                             } else if (p.out_mode == OUT_F32) {
-                                static_cast<float*>(p.out)[o + e] = __uint_as_float(w4[e]);
+                                static_cast<float*>(p.out)[o + e] = __uint_as_float(w4[e & 3]);
                             } else {
-                                atomicAdd(static_cast<float*>(p.out) + o + e, __uint_as_float(w4[e]));
+                                atomicAdd(static_cast<float*>(p.out) + o + e, __uint_as_float(w4[e & 3]));
                             }
                         }
                     }
                 }
             } else if (row_ok) {
                 // unaligned buffers: per-thread scalar path
-                for (int j = 0; j < cvalid; ++j) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (j >= cvalid) break;
                     float x = v[j];
                     if (has_bias) x += p.bias[col + j];
                     if (has_rb) x += p.rowbias[(gn / p.rb_div) * p.rb_ld + col + j];
