@@ -104,7 +104,8 @@ int t2v_bgemm(const T2VMat* A, const T2VMat* B, void* C, int64_t ldc, int64_t c_
  * ResnetBlock2D.norm1/norm2 (per frame: S = B*F), Transformer2DModel.norm (eps 1e-6), TemporalConvLayer /
  * TransformerTemporalModel.norm (per clip: S = B, P = F*H*W) and conv_norm_out (unet_3d_condition.py:239-243,488-490).
  * stat [S][G][2] = (mean, rstd), ab [S][C][2] = per-channel affine with y = act(a x + b) (both saved for backward).
- * workspace: t2v_groupnorm_workspace_bytes(S, P, C) bytes.                                                        */
+ * workspace: t2v_groupnorm_workspace_bytes(S, P, C) bytes, ZERO on entry; every call leaves it zero again, so one
+ * zero-initialised buffer can be reused by all GroupNorm calls of a stream (no memset per call).                  */
 int64_t t2v_groupnorm_workspace_bytes(int32_t S, int64_t P, int32_t C);
 int t2v_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stat, float* ab, void* workspace,
                       int32_t S, int64_t P, int32_t C, int32_t G, float eps, int32_t silu, void* stream);

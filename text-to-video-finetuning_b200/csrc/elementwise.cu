@@ -309,7 +309,20 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __rest
         const int64_t p0 = int64_t(blockIdx.x) * chunk_rows, p1 = min(P, p0 + chunk_rows);
         const uint4* xs = reinterpret_cast<const uint4*>(x + int64_t(s) * P * ld + col0) + cv;
         const int LV = ld >> 3;
-        for (int64_t p = p0 + pl; p < p1; p += lanes) {
+        int64_t p = p0 + pl;
+        for (; p + 3 * lanes < p1; p += 4 * lanes) {  // four 16-byte loads in flight per thread
+            uint4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q[u] = __ldg(xs + (p + u * lanes) * LV);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float v[8];
+                unpack8e(q[u], v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += v[j];
+            }
+        }
+        for (; p < p1; p += lanes) {
             float v[8];
             unpack8e(__ldg(xs + p * LV), v);
 #pragma unroll
@@ -523,12 +536,14 @@ int t2v_copy_cols(const void* src, void* dst, int64_t M, int32_t C, int32_t src_
 }
 int t2v_colsum(const void* x, float* out, int32_t S, int64_t P, int32_t C, void* stream) {
     if (C % 8) return fail(-2, "colsum: C=%d must be a multiple of 8", C);
-    const int64_t want = std::max<int64_t>(1, (4 * 148 + S - 1) / S);
+    // ~2 blocks of 512 threads per SM: the final red.global.add per channel is only ~300 deep, and every thread keeps four
+    // 16-byte loads in flight
+    const int64_t want = std::max<int64_t>(1, (2 * 148 + S - 1) / S);
     const int chunk = int(std::min<int64_t>(P, std::max<int64_t>(16, (P + want - 1) / want)));
     const int chunks = int((P + chunk - 1) / chunk);
     for (int col0 = 0; col0 < C; col0 += 4096) {  // column blocks of <= 4096 channels (512 vectors per block row)
         const int cw = std::min(4096, C - col0);
-        int bs = 256;
+        int bs = 512;
         while (bs < cw / 8) bs += 32;
         launch_pdl(colsum_kernel, dim3(dim3(chunks, S)), dim3(bs), size_t(cw * sizeof(float)), ST, BF(x), out, P, cw, chunk, C, col0);
         if (col0) count_launch();

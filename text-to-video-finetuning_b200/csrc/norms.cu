@@ -26,7 +26,7 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 __device__ __forceinline__ float sigmoidf_(float z) { return 1.0f / (1.0f + __expf(-z)); }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm
-// ONE kernel per direction (plus one memset of the workspace): every block is resident at once (grid <= SMs x occupancy),
+// ONE kernel per direction: every block is resident at once (grid <= SMs x occupancy),
 // so the blocks of a sample can meet at a spin barrier between the two passes over their own pixels:
 //   pass 1  per-channel sums over the block's chunk of pixels, reduced in shared memory, one red.global.add per channel
 //           and block into accum[S][C][2]           fwd: (sum x, sum x^2)      bwd: (sum dz, sum dz*xhat)
@@ -46,8 +46,9 @@ struct GnArgs {
     const float* beta;
     float* stat;              // [S][G][2] (mean, rstd): written by fwd, read by bwd
     float* ab;                // [S][C][2] (a, b) with z = a x + b: written by fwd, read by bwd
-    float* accum;             // [S][C][2] workspace, zeroed before launch
-    unsigned* arrive;         // [S] workspace, zeroed before launch
+    float* accum;             // [S][C][2] workspace (zero on entry, zero again on exit)
+    unsigned* arrive;         // [S] workspace: blocks of the sample that finished pass 1
+    unsigned* done;           // [S] workspace: blocks of the sample that finished reading accum
     float* dgamma;
     float* dbeta;
     int64_t P;
@@ -168,51 +169,71 @@ __global__ void __launch_bounds__(kGnThreads, 1) gn_fused_kernel(const GnArgs g)
     }
     gn_sample_barrier(g.arrive + s, unsigned(g.chunks));
 
-    // ---- finalise (every block, redundantly: 2C floats from L2)
+    // ---- finalise (every block, redundantly): one L2 read per channel, fp64 group combine
     float* t0 = sh;        // fwd: group mean   bwd: sum_c gamma * sum dz
     float* t1 = sh + G;    // fwd: group rstd   bwd: sum_c gamma * sum dz*xhat
-    for (int gi = threadIdx.x; gi < G; gi += kGnThreads) {
-        double a0 = 0, a1 = 0;
-        for (int j = 0; j < cpg; ++j) {
-            const int c = gi * cpg + j;
-            const float2 v = __ldcg(reinterpret_cast<const float2*>(acc) + c);
-            if (MODE == 0) {
-                a0 += v.x;
-                a1 += v.y;
-            } else {
-                a0 += double(g.gamma[c]) * v.x;
-                a1 += double(g.gamma[c]) * v.y;
+    // one warp per group: lanes stride over the group's channels (one L2 read each), fp64 combine through shuffles
+    __shared__ int is_last;
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int gi = warp; gi < G; gi += kGnThreads / 32) {
+            double a0 = 0, a1 = 0;
+            for (int j = lane; j < cpg; j += 32) {
+                const int c = gi * cpg + j;
+                const float2 v = __ldcg(reinterpret_cast<const float2*>(acc) + c);
+                const double w = MODE == 0 ? 1.0 : double(g.gamma[c]);
+                a0 += w * v.x;
+                a1 += w * v.y;
+                if (MODE == 1 && chunk == 0) {
+                    if (g.dbeta) atomicAdd(g.dbeta + c, v.x);
+                    if (g.dgamma) atomicAdd(g.dgamma + c, v.y);
+                }
             }
-        }
-        if (MODE == 0) {
-            const double n = double(g.P) * cpg;
-            const double m = a0 / n;
-            double var = a1 / n - m * m;
-            if (var < 0) var = 0;
-            const float r = float(1.0 / sqrt(var + double(g.eps)));
-            t0[gi] = float(m);
-            t1[gi] = r;
-            if (chunk == 0) {
-                g.stat[(int64_t(s) * G + gi) * 2] = float(m);
-                g.stat[(int64_t(s) * G + gi) * 2 + 1] = r;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                a1 += __shfl_xor_sync(0xffffffffu, a1, o);
             }
-        } else {
-            t0[gi] = float(a0);
-            t1[gi] = float(a1);
+            if (lane == 0) {
+                if (MODE == 0) {
+                    const double n = double(g.P) * cpg;
+                    const double m = a0 / n;
+                    double var = a1 / n - m * m;
+                    if (var < 0) var = 0;
+                    const float r = float(1.0 / sqrt(var + double(g.eps)));
+                    t0[gi] = float(m);
+                    t1[gi] = r;
+                    if (chunk == 0) {
+                        g.stat[(int64_t(s) * G + gi) * 2] = float(m);
+                        g.stat[(int64_t(s) * G + gi) * 2 + 1] = r;
+                    }
+                } else {
+                    t0[gi] = float(a0);
+                    t1[gi] = float(a1);
+                }
+            }
         }
     }
     __syncthreads();
-    if (chunk == 0) {
+    // every read of accum by this block is done: the last block of the sample to get here puts the workspace back to zero
+    // (the contract of the workspace: zero on entry, zero on exit - no memset node per call)
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = atomicAdd(g.done + s, 1u) == unsigned(g.chunks) - 1u;
+    }
+    __syncthreads();
+    if (is_last) {
+        for (int i = threadIdx.x; i < 2 * C; i += kGnThreads) acc[i] = 0.f;
+        if (threadIdx.x == 0) {
+            g.arrive[s] = 0u;
+            g.done[s] = 0u;
+        }
+    }
+    if (MODE == 0 && chunk == 0) {
         for (int c = threadIdx.x; c < C; c += kGnThreads) {
-            if (MODE == 0) {
-                const float aa = t1[c / cpg] * g.gamma[c];
-                g.ab[(int64_t(s) * C + c) * 2] = aa;
-                g.ab[(int64_t(s) * C + c) * 2 + 1] = g.beta[c] - t0[c / cpg] * aa;
-            } else {
-                const float2 v = __ldcg(reinterpret_cast<const float2*>(acc) + c);
-                if (g.dbeta) atomicAdd(g.dbeta + c, v.x);
-                if (g.dgamma) atomicAdd(g.dgamma + c, v.y);
-            }
+            const float aa = t1[c / cpg] * g.gamma[c];
+            g.ab[(int64_t(s) * C + c) * 2] = aa;
+            g.ab[(int64_t(s) * C + c) * 2 + 1] = g.beta[c] - t0[c / cpg] * aa;
         }
     }
     if (!active) return;
@@ -471,7 +492,7 @@ static int gn_launch(GnArgs& g, void* workspace, int S, cudaStream_t st) {
     const size_t ab = gn_accum_bytes(S, g.C);
     g.accum = static_cast<float*>(workspace);
     g.arrive = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + ab);
-    cudaMemsetAsync(workspace, 0, ab + size_t(S) * sizeof(unsigned), st);
+    g.done = g.arrive + S;
     launch_pdl(gn_fused_kernel<MODE>, dim3(S * g.chunks), dim3(kGnThreads), std::max<size_t>(2 * g.C, 2 * g.G) * sizeof(float), st, g);
     count_launch(1);
     return 0;
@@ -485,7 +506,7 @@ extern "C" {
 
 int64_t t2v_groupnorm_workspace_bytes(int32_t S, int64_t P, int32_t C) {
     (void)P;
-    return int64_t(gn_accum_bytes(S, C)) + int64_t(S) * sizeof(unsigned) + 256;
+    return int64_t(gn_accum_bytes(S, C)) + 2 * int64_t(S) * sizeof(unsigned) + 256;
 }
 
 int t2v_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stat, float* ab, void* workspace,

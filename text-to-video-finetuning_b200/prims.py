@@ -100,9 +100,17 @@ def bgemm(a, a_desc, b, b_desc, c, c_desc, M, N, K, Z1, Z2, alpha=1.0, out_mode=
 
 
 # ---------------------------------------------------------------------------------------------- norms
+_gn_ws = {}
+
+
 def groupnorm_ws(S, P, C, device):
-    n = native.lib().t2v_groupnorm_workspace_bytes(S, P, C)
-    return torch.empty((n + 3) // 4, device=device, dtype=torch.float32)
+    """The GroupNorm kernels want zeroed scratch and hand it back zeroed: one buffer per device, grown on demand."""
+    n = (native.lib().t2v_groupnorm_workspace_bytes(S, P, C) + 3) // 4
+    ws = _gn_ws.get(device)
+    if ws is None or ws.numel() < n:
+        ws = torch.zeros(max(n, 1 << 16), device=device, dtype=torch.float32)
+        _gn_ws[device] = ws
+    return ws
 
 
 def groupnorm_fwd(x, gamma, beta, G, eps, silu):
