@@ -157,10 +157,53 @@ def run_reference(args):
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                              "sample": f"{len(times)} fwd+bwd passes of a {frames}-frame clip (oracle port of the reference algorithm, fp32)"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything libraries print (NCCL's version banner, torchrun notes) goes to stderr: stdout carries ONE JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
+def shutdown(world, step=None):
+    """Tear the process group down without hanging: drop the CUDA graph that holds captured NCCL kernels first, and do
+    not let communicator destruction or interpreter teardown block the launcher (bounded by a timer)."""
+    if world <= 1:
+        return
+    import gc
+    import threading
+    sys.stdout.flush()
+    sys.stderr.flush()
+    threading.Timer(20.0, lambda: os._exit(0)).start()
+    try:
+        if step is not None:
+            step._graph = None
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
+    finally:
+        os._exit(0)
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -186,6 +229,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     native.lib()  # fail loudly if the CUDA extension is missing
 
@@ -260,8 +304,7 @@ def main():
     ms, ms_e2e = t.tolist()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown(world, step)
         return
 
     cpu = None
@@ -293,9 +336,8 @@ def main():
         "roofline": dict(roof, share_of_step=(roof["kernel_ms_per_step"] / ms)) if roof else None,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    emit(line)
+    shutdown(world, step)
 
 
 if __name__ == "__main__":

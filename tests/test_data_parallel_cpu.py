@@ -43,7 +43,8 @@ def _worker(rank, world, port, out_path):
         st = S.DataParallelStep(m, L.ddpm_alphas_cumprod(), passes=1)
         loss = st(lat[sl], noise[sl], t[sl], ehs[sl])
     if rank == 0:
-        torch.save({"loss": loss, "grads": {n: p.grad.clone() for n, p in m.named_parameters()}, "arena_total": st.arena.total}, out_path)
+        torch.save({"loss": loss, "grads": {n: p.grad.clone() for n, p in m.named_parameters()}, "arena_total": st.arena.total,
+                    "overlapped": st.buckets.last_overlapped, "blocks": len(st.buckets.ranges)}, out_path)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -57,6 +58,8 @@ def test_two_rank_allreduce_matches_two_clip_oracle(tmp_path):
     port = 29500 + os.getpid() % 2000
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     got = torch.load(out, weights_only=False)
+    # every top-level block's gradient all-reduce was issued from inside the backward pass (4 down + mid + 4 up)
+    assert got["blocks"] == 9 and got["overlapped"] == 9, (got["blocks"], got["overlapped"])
     with torch.device("meta"):
         shapes = UNet3DConditionModel(**SMALL)
     p = {k: v.clone().requires_grad_(True) for k, v in seeded_state_dict(shapes, 3).items()}

@@ -143,15 +143,18 @@ class UNet3DConditionModel(ModelMixin, ConfigMixin):
             else:
                 h = self.transformer_in(h, num_frames=num_frames).sample
 
+        # runtime.GradientBuckets: start a block's share of the gradient all-reduce as soon as its backward is through
+        mark = getattr(self, "_t2v_grad_hook", None)
         h, keep = ops.fork(h)
         skips = [keep]
-        for block in self.down_blocks:
-            h, res = block(h, sc)
+        for i, block in enumerate(self.down_blocks):
+            h, res = block(ops.grad_mark(h, mark, f"down_blocks.{i}"), sc)
             skips.extend(res)
 
-        h = self.mid_block(h, sc)
+        h = self.mid_block(ops.grad_mark(h, mark, "mid_block"), sc)
 
         for i, block in enumerate(self.up_blocks):
+            h = ops.grad_mark(h, mark, f"up_blocks.{i}")
             n = len(block.resnets)
             res, skips = skips[-n:], skips[:-n]
             size = None

@@ -125,6 +125,26 @@ def fork(x, n=2):
     return _Fork.apply(x, n)
 
 
+class _GradMark(Function):
+    """Identity whose backward first calls `hook(key)`: placed on the main activation path at the input of a block, it
+    fires once every gradient of that block (and of everything after it in forward order) has been launched - which is
+    when runtime.GradientBuckets starts that block's share of the gradient all-reduce."""
+
+    @staticmethod
+    def forward(ctx, x, hook, key):
+        ctx.hook, ctx.key = hook, key
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        ctx.hook(ctx.key)
+        return g, None, None
+
+
+def grad_mark(x, hook, key):
+    return _GradMark.apply(x, hook, key) if hook is not None and x.requires_grad else x
+
+
 # ---------------------------------------------------------------------------------------------------- conv / linear
 class _Conv(Function):
     """y = conv(x, W) + bias + rowbias[n // rb_div] + residual on the tcgen05 implicit-GEMM kernel."""

@@ -116,6 +116,68 @@ def allreduce_gradients(arena, world_size=None, average=True):
     return dist.all_reduce(arena.grad, op=dist.ReduceOp.SUM, async_op=False)
 
 
+class GradientBuckets:
+    """Overlaps the gradient all-reduce with the backward pass.
+
+    The flat gradient buffer holds the weight matrices in registration order, so the matrices of one top-level block
+    (down_blocks.i / mid_block / up_blocks.i) are one contiguous range.  The model marks the input of every block
+    (ops.grad_mark); when the backward pass reaches a mark, that block's range is complete and its all-reduce is
+    issued asynchronously (NCCL runs it on its own stream, also inside a captured CUDA graph) while the rest of the
+    backward keeps the SMs busy.  `finish()` reduces what is left (stem, time embedding, all vectors) and joins."""
+
+    def __init__(self, arena, module, group=None):
+        self.arena, self.module, self.group = arena, module, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        off_of = {id(p): o for p, o in zip(arena.params, arena.offsets)}
+        ranges = {}
+        for name, p in module.named_parameters():
+            if p.dim() < 2 or id(p) not in off_of:
+                continue
+            parts = name.split(".")
+            key = ".".join(parts[:2]) if parts[0] in ("down_blocks", "up_blocks") else parts[0]
+            lo, hi = off_of[id(p)], off_of[id(p)] + _align(p.numel())
+            a, b = ranges.get(key, (lo, hi))
+            ranges[key] = (min(a, lo), max(b, hi))
+        self.ranges = {k: v for k, v in ranges.items() if k.startswith(("down_blocks.", "up_blocks.")) or k == "mid_block"}
+        spans = sorted(self.ranges.values())
+        for (a0, b0), (a1, b1) in zip(spans, spans[1:]):
+            if b0 > a1:
+                raise RuntimeError("block gradient ranges overlap: parameters are not laid out in registration order")
+        self.armed = False
+        self._done, self._works = set(), []
+        use_avg = dist.is_initialized() and dist.get_backend(group) == "nccl"
+        self._op = dist.ReduceOp.AVG if use_avg else dist.ReduceOp.SUM
+
+    def install(self):
+        self.module._t2v_grad_hook = self.on_block_done
+
+    def _reduce(self, a, b):
+        if b <= a:
+            return
+        view = self.arena.grad[a:b]
+        if self._op == dist.ReduceOp.SUM:
+            view.div_(self.world)
+        self._works.append(dist.all_reduce(view, op=self._op, group=self.group, async_op=True))
+
+    def on_block_done(self, key):
+        if not self.armed or key in self._done or key not in self.ranges:
+            return
+        self._done.add(key)
+        self._reduce(*self.ranges[key])
+
+    def finish(self):
+        """Reduce every range no mark has covered, then make the current stream wait for all of it."""
+        covered = sorted(self.ranges[k] for k in self._done)
+        pos = 0
+        for a, b in covered + [(self.arena.total, self.arena.total)]:
+            self._reduce(pos, a)
+            pos = max(pos, b)
+        for w in self._works:
+            w.wait()
+        self.last_overlapped = len(self._done)   # blocks whose all-reduce started inside the backward pass
+        self._works, self._done, self.armed = [], set(), False
+
+
 class GraphedStep:
     """Captures `fn(*static_inputs)` (forward + backward of one clip batch) into a CUDA graph and replays it.
 

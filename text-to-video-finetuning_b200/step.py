@@ -1,10 +1,13 @@
 """Training-step glue of the hot path: the B200-native equivalents of the reference's
 `tensor_to_vae_latent` (train.py:339-347), `sample_noise` (:349-358), `noise_scheduler.add_noise` (:760) and the
 epsilon-MSE of `finetune_unet` (:720-836), plus the data-parallel step object used by train.py and bench.py."""
+import os
+
 import torch
+import torch.distributed as dist
 
 from . import ops, prims
-from .runtime import GraphedStep, ParamArena, allreduce_gradients
+from .runtime import GradientBuckets, GraphedStep, ParamArena, allreduce_gradients
 
 
 def ddpm_alphas_cumprod(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, device=None):
@@ -52,16 +55,27 @@ class DataParallelStep:
         self.use_graph = use_graph
         self.sync_gradients = True   # set False to run fwd+bwd only (profiling on a single rank)
         self._graph = None
+        # world > 1: per-block gradient all-reduces are issued from inside the backward pass (overlap), see GradientBuckets
+        self.buckets = None
+        if (self.arena is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+                and not os.environ.get("T2V_NO_OVERLAP")):
+            self.buckets = GradientBuckets(self.arena, unet)
+            self.buckets.install()
 
     def _fwd_bwd(self, latents, noise, timesteps, text):
         if self.arena is not None:
             self.arena.zero_grads()
             self.arena.refresh_shadow()
         total = None
-        for _ in range(self.passes):
+        overlap = self.buckets is not None and self.sync_gradients
+        for i in range(self.passes):
             loss = finetune_loss(self.unet, latents, noise, timesteps, text, self.abar)
+            if overlap:
+                self.buckets.armed = i == self.passes - 1   # gradients are final only in the last pass
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
+        if overlap:
+            self.buckets.finish()
         return total
 
     def __call__(self, latents, noise, timesteps, encoder_hidden_states):
@@ -74,6 +88,6 @@ class DataParallelStep:
             loss = self._graph(*args)
         else:
             loss = self._fwd_bwd(*args)
-        if self.arena is not None and self.sync_gradients:
+        if self.arena is not None and self.sync_gradients and self.buckets is None:
             allreduce_gradients(self.arena)
         return loss
