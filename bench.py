@@ -126,6 +126,16 @@ def oracle_pass_seconds(sd_cpu, cfg, frames, threads, reps=1):
     return best, float(loss)
 
 
+def gemm_traffic():
+    """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum averaged over the
+    launches of one step) from the committed ncu capture profiles/r1_gemm_traffic.json; None if the file is absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def run_reference(args):
     """--impl reference: the reference algorithm (oracle port of train.py:739-834 + UNet wiring) on host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -266,7 +276,7 @@ def main():
         flops = (PASS_TFLOP_PER_CLIP if not args.small else float("nan")) * B
         ach = flops / (gemm_ms / 1e3) if gemm_ms > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM conv / linear / attention products)",
-                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": gemm_traffic(),
                 "launches": n_gemm, "distinct_shapes": len(calls), "kernel_ms_per_step": gemm_ms, "share_of_step": None,
                 "algorithmic_tflop_per_step": flops, "peak_source": how}
 

@@ -194,6 +194,22 @@ def test_fused_projection_attention_matches_unfused(cross):
         close(x, y, 1.5e-2, f"fused attention d{name}")
 
 
+@pytest.mark.parametrize("p,scale", [(0.1, 1.0), (0.5, 0.25), (0.0, 1.0)])
+def test_dropout_scale_add_mask_is_bit_exact(p, scale):
+    """The dropout mask is a pure function of (seed, element index): the kernel and its torch restatement must keep
+    exactly the same elements (integer hash => bit-exact mask), values agree to bf16 rounding."""
+    prims, ref = _mods()
+    g = _gen(9)
+    x, base = rnd(g, 333, 640), rnd(g, 333, 640)
+    for seed in (1, 0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF):
+        y, y_r = prims.dropout_scale_add(x, None, p, scale, seed), ref.dropout_scale_add(x, None, p, scale, seed)
+        assert torch.equal(y == 0, y_r == 0), "dropout masks differ"
+        close(y, y_r, 1e-2, "dropout values")
+        kept = (y != 0).float().mean().item()
+        assert abs(kept - (1.0 - p)) < 0.01, kept
+        close(prims.dropout_scale_add(x, base, p, scale, seed), ref.dropout_scale_add(x, base, p, scale, seed), 1e-2, "dropout + base")
+
+
 def test_latent_boundary_and_loss():
     prims, ref = _mods()
     g = _gen(8)
