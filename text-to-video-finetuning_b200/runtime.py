@@ -54,7 +54,8 @@ class ParamArena:
                 self.master[o:o + n].copy_(phys.reshape(-1))
                 view = torch.as_strided(self.master, p.shape, p.stride(), o)
                 p.data = view
-                p.grad = torch.as_strided(self.grad, p.shape, p.stride(), o)
+                # frozen parameters keep grad None, so optimizers skip them exactly as they do in the reference
+                p.grad = torch.as_strided(self.grad, p.shape, p.stride(), o) if p.requires_grad else None
                 if p.dim() >= 2:
                     p._t2v_shadow = self.shadow[o:o + n].view(ops._phys(view).shape)
         self.offsets = offs
@@ -95,9 +96,12 @@ class ParamArena:
         self.grad.zero_()
 
     def reattach_grads(self):
-        """optimizer.zero_grad(set_to_none=True) drops the views; put them back."""
+        """optimizer.zero_grad(set_to_none=True) drops the views; put them back (trainable parameters only: a frozen
+        parameter's grad stays None, which is what makes torch optimizers skip it - no weight decay on frozen weights)."""
         for p, o in zip(self.params, self.offsets):
-            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
+            if not p.requires_grad:
+                p.grad = None
+            elif p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
                 p.grad = torch.as_strided(self.grad, p.shape, p.stride(), o)
 
     def grad_norm(self):

@@ -180,8 +180,9 @@ def main(
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    dev = torch.device(kwargs.get("device") or f"cuda:{local}")   # "device" is a test hook (CPU runs use emulated primitives)
+    if dev.type == "cuda":
+        torch.cuda.set_device(dev)
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -230,7 +231,8 @@ def main(
     elif "synthetic" in kinds:
         td = train_data or {}
         dataset = SyntheticLatents(n=td.get("n", 64), frames=td.get("n_sample_frames", 16),
-                                   hw=(td.get("height", 256) // 8, td.get("width", 256) // 8))
+                                   hw=(td.get("height", 256) // 8, td.get("width", 256) // 8),
+                                   text_dim=unet.config.cross_attention_dim)
     else:
         raise NotImplementedError(f"dataset_types={kinds}: raw-video datasets need decord + VAE/text encoders (SURVEY 8(f)); "
                                   "use cached_latent_dir or dataset_types: ['synthetic']")
