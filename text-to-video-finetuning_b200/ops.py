@@ -9,6 +9,8 @@ Conventions
     the Functions return None for them.  This is what lets the data-parallel step all-reduce one flat buffer.
   * fan-out of an activation is made explicit with `fork`, so gradient fan-in runs in our add kernel.
 """
+import os
+
 import torch
 from torch.autograd import Function
 
@@ -125,6 +127,56 @@ def fork(x, n=2):
     return _Fork.apply(x, n)
 
 
+# ------------------------------------------------------------------------------------------- side stream for weight gradients
+# Parameter gradients are leaves of the backward pass: nothing downstream in backward reads them.  Their kernels (wgrad
+# GEMM + bias column sums, ~900 short launches per step) therefore run on a second stream, forked after the producer of dy
+# and joined when the backward pass ends (and before a block's gradient range is all-reduced): on the GPU - and as a
+# parallel branch of the captured CUDA graph - they fill the launch gaps and tails of the latency-bound main chain.
+class _Side:
+    enabled = not os.environ.get("T2V_NO_SIDE_WGRAD")
+    streams = {}          # device index -> side stream
+    pending = {}          # device index -> (main stream, tensors kept alive until the join)
+
+
+def _side_join(dev_index):
+    ent = _Side.pending.pop(dev_index, None)
+    if ent is not None:
+        main, _refs = ent
+        main.wait_stream(_Side.streams[dev_index])   # _refs die here: their memory is only reused after the join is enqueued
+
+
+def join_side_streams():
+    """Make the main stream(s) wait for every parameter-gradient kernel issued so far."""
+    for d in list(_Side.pending):
+        _side_join(d)
+
+
+def _run_param_grads(fn, *keep):
+    """Run fn() (kernels that only write parameter gradients) on the side stream of the current device."""
+    t = keep[0]
+    if not (_Side.enabled and t.is_cuda):
+        fn()
+        return
+    d = t.device.index
+    main = torch.cuda.current_stream(t.device)
+    side = _Side.streams.get(d)
+    if side is None:
+        side = _Side.streams[d] = torch.cuda.Stream(device=t.device)
+    ent = _Side.pending.get(d)
+    if ent is None:
+        ent = _Side.pending[d] = (main, [])
+        # join when this backward pass ends, whoever started it (also inside CUDA-graph capture and checkpoint recomputes)
+        torch.autograd.Variable._execution_engine.queue_callback(lambda: _side_join(d))
+    elif ent[0] != main:
+        _side_join(d)
+        ent = _Side.pending[d] = (main, [])
+        torch.autograd.Variable._execution_engine.queue_callback(lambda: _side_join(d))
+    side.wait_stream(main)                 # fork: dy (and x) are complete on the main stream at this point
+    with torch.cuda.stream(side):
+        fn()
+    ent[1].append(keep)                    # keep the operands alive: the caching allocator must not hand them out early
+
+
 class _GradMark(Function):
     """Identity whose backward first calls `hook(key)`: placed on the main activation path at the input of a block, it
     fires once every gradient of that block (and of everything after it in forward order) has been launched - which is
@@ -137,6 +189,7 @@ class _GradMark(Function):
 
     @staticmethod
     def backward(ctx, g):
+        join_side_streams()   # the block's parameter gradients must be complete before its range is all-reduced
         ctx.hook(ctx.key)
         return g, None, None
 
@@ -184,30 +237,35 @@ class _Conv(Function):
         if alpha != 1.0:
             assert rb_shape is None and bias is None, "alpha != 1 is only used by bias-free low-rank branches"
             dy = prims.scale_bf16(dy, alpha)
-        d_rowbias = None
+        d_rowbias = d_rowbias_full = None
         if rb_shape is not None and ctx.needs_input_grad[3]:
-            d_rowbias = torch.zeros(rb_shape, device=dy.device, dtype=torch.float32)
-            prims.colsum(dy, d_rowbias, rb_shape[0], (N // rb_shape[0]) * Ho * Wo, Co)
-        if bias is not None and bias.requires_grad:
-            gb = grad_vec(bias)
-            if cout_pad:
-                tmp = torch.zeros(Co, device=dy.device, dtype=torch.float32)
-                prims.colsum(dy, tmp.view(1, Co), 1, N * Ho * Wo, Co)
-                gb += tmp[:Co - cout_pad]
-                if d_rowbias is not None:
-                    d_rowbias = d_rowbias[:, :Co - cout_pad].contiguous()
-            elif d_rowbias is not None:
-                prims.colsum_f32(d_rowbias, gb)
-            else:
-                prims.colsum(dy, gb.view(1, Co), 1, N * Ho * Wo, Co)
-        if weight.requires_grad:
-            if cin_pad or cout_pad:
-                tmp = torch.zeros(w.shape, device=dy.device, dtype=torch.float32)
-                prims.conv_wgrad(x, dy, tmp, stride, pads)
-                g = grad_phys(weight)
-                g += tmp[:g.shape[0], :, :, :g.shape[3]]
-            else:
-                prims.conv_wgrad(x, dy, grad_phys(weight), stride, pads)
+            d_rowbias_full = torch.zeros(rb_shape, device=dy.device, dtype=torch.float32)
+            prims.colsum(dy, d_rowbias_full, rb_shape[0], (N // rb_shape[0]) * Ho * Wo, Co)
+            d_rowbias = d_rowbias_full[:, :Co - cout_pad].contiguous() if cout_pad else d_rowbias_full
+        # parameter gradients (bias column sums, weight gradient) are leaves: they run on the side stream
+        gb = grad_vec(bias) if (bias is not None and bias.requires_grad) else None
+        gw = grad_phys(weight) if weight.requires_grad else None
+
+        def param_grads():
+            if gb is not None:
+                if cout_pad:
+                    tmp = torch.zeros(Co, device=dy.device, dtype=torch.float32)
+                    prims.colsum(dy, tmp.view(1, Co), 1, N * Ho * Wo, Co)
+                    gb.add_(tmp[:Co - cout_pad])
+                elif d_rowbias_full is not None:
+                    prims.colsum_f32(d_rowbias_full, gb)
+                else:
+                    prims.colsum(dy, gb.view(1, Co), 1, N * Ho * Wo, Co)
+            if gw is not None:
+                if cin_pad or cout_pad:
+                    tmp = torch.zeros(w.shape, device=dy.device, dtype=torch.float32)
+                    prims.conv_wgrad(x, dy, tmp, stride, pads)
+                    gw.add_(tmp[:gw.shape[0], :, :, :gw.shape[3]])
+                else:
+                    prims.conv_wgrad(x, dy, gw, stride, pads)
+
+        if gb is not None or gw is not None:
+            _run_param_grads(param_grads, dy, x, d_rowbias_full)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = prims.conv_dgrad(dy, w, (x.shape[1], x.shape[2]), stride, pads)
