@@ -229,7 +229,7 @@ def main():
         return run_reference(args)
 
     import torch.distributed as dist
-    from t2v_b200 import native, prims
+    from t2v_b200 import native
     from t2v_b200 import step as S
 
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -4,7 +4,6 @@ own timestep - SURVEY section 4).  Native primitives are emulated (tests only)."
 import os
 import sys
 
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp

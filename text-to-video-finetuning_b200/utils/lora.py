@@ -15,7 +15,7 @@ layer:
 """
 import json
 import os
-from typing import Dict, List, Optional, Set, Tuple, Type, Union
+from typing import List, Optional, Set, Type, Union
 
 import torch
 import torch.nn as nn
