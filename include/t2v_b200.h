@@ -96,6 +96,25 @@ typedef struct {
 int t2v_bgemm(const T2VMat* A, const T2VMat* B, void* C, int64_t ldc, int64_t c_stride_z1, int64_t c_stride_z2,
               int32_t M, int32_t N, int32_t K, int32_t Z1, int32_t Z2, float alpha, int32_t out_mode, void* stream);
 
+/* Fused attention (head_dim 64): O = softmax(Q K^T / 8) V per (batch, head) without materialising the score matrix,
+ * plus its backward; replaces the t2v_bgemm / t2v_softmax composition for Transformer2DModel's self- and cross-attention
+ * (diffusers AttnProcessor2_0 -> F.scaled_dot_product_attention in the reference, train.py:138-152).
+ * Operands are [Nb][L][heads*64] with arbitrary row pitch (*_ld) and batch stride (*_bs) in elements, so q / k / v and
+ * dq / dk / dv may be column slices of fused QKV / K|V projections.  o and dout are [Nb][Lq][heads*64] (o_ld, o_bs).
+ * lse: fp32 [Nb][heads][Lq] (natural-log sum-exp of the scaled scores), written by fwd, read by bwd.
+ * delta_ws: fp32 scratch [Nb][heads][Lq].  dkv_ws: fp32 scratch [2][Nb][Lk][heads*64], ZERO on entry, required only when
+ * t2v_flash_attn_bwd_splits(...) > 1 (few keys, many queries: cross-attention); dK / dV are then left in dkv_ws (fp32)
+ * for the caller to cast, and dk / dv are not written.                                                               */
+int t2v_flash_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int32_t Nb, int32_t heads, int32_t Lq,
+                       int32_t Lk, int32_t head_dim, int64_t q_ld, int64_t q_bs, int64_t k_ld, int64_t k_bs, int64_t v_ld,
+                       int64_t v_bs, int64_t o_ld, int64_t o_bs, void* stream);
+int32_t t2v_flash_attn_bwd_splits(int32_t Nb, int32_t heads, int32_t Lq, int32_t Lk);
+int t2v_flash_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, void* dq,
+                       void* dk, void* dv, float* delta_ws, float* dkv_ws, int32_t Nb, int32_t heads, int32_t Lq, int32_t Lk,
+                       int32_t head_dim, int64_t q_ld, int64_t q_bs, int64_t k_ld, int64_t k_bs, int64_t v_ld, int64_t v_bs,
+                       int64_t o_ld, int64_t o_bs, int64_t dq_ld, int64_t dq_bs, int64_t dk_ld, int64_t dk_bs, int64_t dv_ld,
+                       int64_t dv_bs, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * HBM-bound kernels (128-bit accesses, fp32 statistics, warp-shuffle reductions).
  */

@@ -298,6 +298,30 @@ def attn_small_bwd(q, k, v, do, dq, dk, dv, addr):
     return dq, dk, dv
 
 
+def _heads_view(t, heads):
+    Nb, L, C = t.shape
+    return t.float().reshape(Nb, L, heads, C // heads).transpose(1, 2)
+
+
+def flash_attn_fwd(q, k, v, heads):
+    """softmax(q k^T / sqrt(d)) v per (batch, head) and the log-sum-exp of the scaled scores (natural log)."""
+    Nb, Lq, C = q.shape
+    s = _heads_view(q, heads) @ _heads_view(k, heads).transpose(-1, -2) * (C // heads) ** -0.5
+    o = (torch.softmax(s, -1) @ _heads_view(v, heads)).transpose(1, 2).reshape(Nb, Lq, C)
+    return o.to(BF), torch.logsumexp(s, -1)
+
+
+@torch.enable_grad()
+def flash_attn_bwd(q, k, v, o, do, lse, heads, dq, dk, dv):
+    Nb, Lq, C = q.shape
+    qf, kf, vf = (t.float().detach().clone().requires_grad_(True) for t in (q, k, v))
+    s = _heads_view(qf, heads) @ _heads_view(kf, heads).transpose(-1, -2) * (C // heads) ** -0.5
+    out = (torch.softmax(s, -1) @ _heads_view(vf, heads)).transpose(1, 2).reshape(Nb, Lq, C)
+    gq, gk, gv = torch.autograd.grad(out, (qf, kf, vf), do.float())
+    for g, dst in ((gq, dq), (gk, dk), (gv, dv)):
+        dst.copy_(g.to(dst.dtype))
+
+
 def timestep_embedding(t, dim):
     half = dim // 2
     f = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half)

@@ -437,8 +437,21 @@ def _rup8(n):
     return (n + 7) // 8 * 8
 
 
+class _Flash:
+    # Fused attention kernels (csrc/flash_attn.cu): verified stand-alone on B200 (profiles/r1_flash_attn_experiment.txt);
+    # opt-in until the end-to-end GPU parity suite has run with them (tests/test_flash_attn.py, T2V_FLASH_ATTN=1).
+    enabled = bool(os.environ.get("T2V_FLASH_ATTN"))
+
+
+def _use_flash(q, heads):
+    return _Flash.enabled and q.shape[-1] // heads == 64
+
+
 def _attn_core_fwd(q, k, v, heads):
-    """q [Nb, Lq, C], k/v [Nb, Lk, C]: row-contiguous views (arbitrary row pitch).  Returns (o contiguous, p)."""
+    """q [Nb, Lq, C], k/v [Nb, Lk, C]: row-contiguous views (arbitrary row pitch).  Returns (o contiguous, aux) where aux is
+    the bf16 probability tensor P of the unfused path, or the fp32 log-sum-exp of the fused (flash) path."""
+    if _use_flash(q, heads):
+        return prims.flash_attn_fwd(q, k, v, heads)
     Nb, Lq, C = q.shape
     Lk = k.shape[1]
     D = C // heads
@@ -454,8 +467,12 @@ def _attn_core_fwd(q, k, v, heads):
     return o, p
 
 
-def _attn_core_bwd(q, k, v, p, do, dq, dk, dv, heads):
-    """Gradients of _attn_core_fwd written into the (row-contiguous, possibly column-sliced) views dq / dk / dv."""
+def _attn_core_bwd(q, k, v, p, do, dq, dk, dv, heads, o=None):
+    """Gradients of _attn_core_fwd written into the (row-contiguous, possibly column-sliced) views dq / dk / dv.
+    `p` is the aux tensor of the forward pass; an fp32 aux is the log-sum-exp of the fused path (which also needs `o`)."""
+    if p.dtype == torch.float32 and p.dim() == 3:
+        prims.flash_attn_bwd(q, k, v, o, do, p, heads, dq, dk, dv)
+        return
     Nb, Lq, C = q.shape
     Lk = k.shape[1]
     D = C // heads
@@ -495,15 +512,15 @@ class _Attention(Function):
     @staticmethod
     def forward(ctx, q, k, v, heads):
         o, p = _attn_core_fwd(q, k, v, heads)
-        ctx.save_for_backward(q, k, v, p)
+        ctx.save_for_backward(q, k, v, p, o)
         ctx.heads = heads
         return o
 
     @staticmethod
     def backward(ctx, do):
-        q, k, v, p = ctx.saved_tensors
+        q, k, v, p, o = ctx.saved_tensors
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-        _attn_core_bwd(q, k, v, p, _cont(do), dq, dk, dv, ctx.heads)
+        _attn_core_bwd(q, k, v, p, _cont(do), dq, dk, dv, ctx.heads, o)
         return dq, dk, dv, None
 
 
@@ -525,13 +542,13 @@ class _AttentionFused(Function):
             C = qkv.shape[-1]
             q, k, v = qkv, kv[..., :C], kv[..., C:]
         o, p = _attn_core_fwd(q, k, v, heads)
-        ctx.save_for_backward(qkv, kv, p)
+        ctx.save_for_backward(qkv, kv, p, o)
         ctx.heads = heads
         return o
 
     @staticmethod
     def backward(ctx, do):
-        qkv, kv, p = ctx.saved_tensors
+        qkv, kv, p, o = ctx.saved_tensors
         dqkv = torch.empty_like(qkv)
         if kv is None:
             C = qkv.shape[-1] // 3
@@ -543,7 +560,7 @@ class _AttentionFused(Function):
             dkv = torch.empty_like(kv)
             q, k, v = qkv, kv[..., :C], kv[..., C:]
             dq, dk, dv = dqkv, dkv[..., :C], dkv[..., C:]
-        _attn_core_bwd(q, k, v, p, _cont(do), dq, dk, dv, ctx.heads)
+        _attn_core_bwd(q, k, v, p, _cont(do), dq, dk, dv, ctx.heads, o)
         return dqkv, dkv, None
 
 

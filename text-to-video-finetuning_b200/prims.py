@@ -99,6 +99,44 @@ def bgemm(a, a_desc, b, b_desc, c, c_desc, M, N, K, Z1, Z2, alpha=1.0, out_mode=
                                         M, N, K, Z1, Z2, float(alpha), out_mode, _stream()))
 
 
+def flash_attn_fwd(q, k, v, heads):
+    """Fused attention forward (head_dim 64).  q [Nb, Lq, C], k / v [Nb, Lk, C] bf16 row-contiguous views (column slices of
+    fused projections allowed).  Returns o [Nb, Lq, C] bf16 and lse [Nb, heads, Lq] fp32."""
+    for t in (q, k, v):
+        assert t.dtype == torch.bfloat16 and t.is_cuda and t.dim() == 3 and t.stride(2) == 1, (t.dtype, t.shape, t.stride())
+    Nb, Lq, C = q.shape
+    Lk = k.shape[1]
+    o = torch.empty((Nb, Lq, C), device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty((Nb, heads, Lq), device=q.device, dtype=torch.float32)
+    native.check(native.lib().t2v_flash_attn_fwd(_p(q), _p(k), _p(v), _p(o), _p(lse), Nb, heads, Lq, Lk, C // heads, q.stride(1),
+                                                 q.stride(0), k.stride(1), k.stride(0), v.stride(1), v.stride(0), o.stride(1),
+                                                 o.stride(0), _stream()))
+    return o, lse
+
+
+def flash_attn_bwd(q, k, v, o, do, lse, heads, dq, dk, dv):
+    """Gradients of flash_attn_fwd written into the (possibly column-sliced) views dq / dk / dv."""
+    for t in (q, k, v, dq, dk, dv):
+        assert t.dtype == torch.bfloat16 and t.is_cuda and t.dim() == 3 and t.stride(2) == 1, (t.dtype, t.shape, t.stride())
+    _chk_bf16(o, do)
+    _chk_f32(lse)
+    Nb, Lq, C = q.shape
+    Lk = k.shape[1]
+    delta = torch.empty((Nb, heads, Lq), device=q.device, dtype=torch.float32)
+    splits = native.lib().t2v_flash_attn_bwd_splits(Nb, heads, Lq, Lk)
+    ws = torch.zeros((2, Nb, Lk, C), device=q.device, dtype=torch.float32) if splits > 1 else None
+    native.check(native.lib().t2v_flash_attn_bwd(_p(q), _p(k), _p(v), _p(o), _p(do), _p(lse), _p(dq), _p(dk), _p(dv), _p(delta), _p(ws),
+                                                 Nb, heads, Lq, Lk, C // heads, q.stride(1), q.stride(0), k.stride(1), k.stride(0),
+                                                 v.stride(1), v.stride(0), o.stride(1), o.stride(0), dq.stride(1), dq.stride(0),
+                                                 dk.stride(1), dk.stride(0), dv.stride(1), dv.stride(0), _stream()))
+    if ws is not None:   # few keys, many queries: the kernel reduced fp32 partials; round once into the bf16 gradients
+        for dst, src in ((dk, ws[0]), (dv, ws[1])):
+            if dst.is_contiguous():
+                cast_f32_bf16(src, dst)
+            else:
+                dst.copy_(cast_f32_bf16(src))
+
+
 # ---------------------------------------------------------------------------------------------- norms
 _gn_ws = {}
 
