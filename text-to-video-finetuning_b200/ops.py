@@ -141,8 +141,8 @@ class _Side:
 def _side_join(dev_index):
     ent = _Side.pending.pop(dev_index, None)
     if ent is not None:
-        main, _refs = ent
-        main.wait_stream(_Side.streams[dev_index])   # _refs die here: their memory is only reused after the join is enqueued
+        main = ent[0]
+        main.wait_stream(_Side.streams[dev_index])   # ent[1] (operand refs) dies here: memory is reused only after the join is enqueued
 
 
 def join_side_streams():
@@ -162,14 +162,13 @@ def _run_param_grads(fn, *keep):
     side = _Side.streams.get(d)
     if side is None:
         side = _Side.streams[d] = torch.cuda.Stream(device=t.device)
+    task = torch._C._current_graph_task_id()   # one id per backward pass (-1 outside of one)
     ent = _Side.pending.get(d)
-    if ent is None:
-        ent = _Side.pending[d] = (main, [])
+    if ent is None or ent[0] != main or ent[2] != task:
+        if ent is not None:      # left over from another stream / an aborted backward pass
+            _side_join(d)
+        ent = _Side.pending[d] = (main, [], task)
         # join when this backward pass ends, whoever started it (also inside CUDA-graph capture and checkpoint recomputes)
-        torch.autograd.Variable._execution_engine.queue_callback(lambda: _side_join(d))
-    elif ent[0] != main:
-        _side_join(d)
-        ent = _Side.pending[d] = (main, [])
         torch.autograd.Variable._execution_engine.queue_callback(lambda: _side_join(d))
     side.wait_stream(main)                 # fork: dy (and x) are complete on the main stream at this point
     with torch.cuda.stream(side):
