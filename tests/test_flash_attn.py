@@ -2,9 +2,9 @@
 
 CPU (always): the host logic of the fused path - dispatch, saved tensors, column-sliced fused QKV / K|V operands and
 gradient layouts - over the emulated primitives must reproduce the unfused path exactly.
-GPU (opt-in, T2V_FLASH_ATTN=1, until the path has been through one full GPU suite run): the kernels through the C ABI
-vs the fp32 restatement, and the end-to-end UNet parity of tests/test_unet_gpu.py with the fused path switched on.
-The same kernels passed a stand-alone run of these checks on B200 (profiles/r1_flash_attn_experiment.txt)."""
+GPU (opt-in, T2V_FLASH_ATTN=1, until the path has been through one full GPU suite + bench run): the kernels through the
+C ABI vs the fp32 restatement, and the end-to-end UNet parity of tests/test_unet_gpu.py with the fused path switched on.
+Both passed on B200 at the end of round 1 (profiles/r1_flash_attn_suite.txt, profiles/r1_flash_attn_experiment.txt)."""
 import os
 
 import pytest

@@ -6,8 +6,9 @@
 // STATUS (end of round 1): verified on B200 through this C ABI against a PyTorch fp32 attention - values, log-sum-exp and
 // all three gradients, fused-pitch operands, ragged lengths, split-query cross-attention; worst rel-to-max error 4.7e-3,
 // 96 us forward / 328 us backward for 16 frames x 1024 tokens x 5 heads vs 268 / 431 us unfused
-// (profiles/r1_flash_attn_experiment.txt) - but measured only stand-alone: the model uses it when T2V_FLASH_ATTN=1
-// (ops._use_flash), default off until the end-to-end parity suite has run with it on a GPU.
+// (profiles/r1_flash_attn_experiment.txt), and with T2V_FLASH_ATTN=1 the end-to-end UNet parity tests pass on B200
+// (profiles/r1_flash_attn_suite.txt).  Not yet benchmarked inside the step: the model uses it only when T2V_FLASH_ATTN=1
+// (ops._use_flash).
 //
 // FlashAttention-2 blocking on warp-level tensor-core MMAs (mma.sync.m16n8k16 + ldmatrix, the helpers of attn_small.cu),
 // cp.async double-buffered K/V tiles, online softmax in the accumulator registers.

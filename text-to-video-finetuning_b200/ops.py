@@ -437,8 +437,8 @@ def _rup8(n):
 
 
 class _Flash:
-    # Fused attention kernels (csrc/flash_attn.cu): verified stand-alone on B200 (profiles/r1_flash_attn_experiment.txt);
-    # opt-in until the end-to-end GPU parity suite has run with them (tests/test_flash_attn.py, T2V_FLASH_ATTN=1).
+    # Fused attention kernels (csrc/flash_attn.cu): kernel and end-to-end UNet parity verified on B200 with the flag on
+    # (profiles/r1_flash_attn_*.txt); opt-in until the full GPU suite and the bench have run with them.
     enabled = bool(os.environ.get("T2V_FLASH_ATTN"))
 
 
