@@ -203,6 +203,12 @@ int t2v_attn_small_bwd(const void* q, const void* k, const void* v, const void* 
                        int32_t inner, int64_t outer_rows, int64_t inner_rows, int64_t seq_rows, int64_t ld_in, int64_t ld_out,
                        int32_t heads, int32_t L, int32_t D, void* stream);
 
+/* Fused AdamW over n contiguous fp32 parameters of the flat arena (torch.optim.AdamW semantics, the optimizer the reference
+ * builds at train.py:616-623): updates p, m, v in place from g * grad_scale, optionally writes the bf16 compute copy of p
+ * (shadow_bf16, may be NULL) and zeroes g (zero_grad != 0).  step counts optimizer steps from 1 (bias correction).        */
+int t2v_adamw_step(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int32_t step, float grad_scale, int32_t zero_grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -216,6 +216,22 @@ def dropout_scale_add(x, base, p, scale, seed):
     return y.to(BF)
 
 
+@torch.no_grad()
+def adamw_step(p, g, m, v, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, zero_grad=False):
+    """torch.optim.AdamW's single-tensor update, on flat ranges (same arithmetic order as the kernel)."""
+    gs = g * grad_scale
+    p.mul_(1.0 - lr * weight_decay)
+    m.mul_(beta1).add_(gs, alpha=1.0 - beta1)
+    v.mul_(beta2).addcmul_(gs, gs, value=1.0 - beta2)
+    bc1 = 1.0 - beta1 ** step
+    bc2_sqrt = (1.0 - beta2 ** step) ** 0.5
+    p.addcdiv_(m, v.sqrt() / bc2_sqrt + eps, value=-(lr / bc1))
+    if shadow is not None:
+        shadow.copy_(p)
+    if zero_grad:
+        g.zero_()
+
+
 def add_f32(a, b):
     return a + b
 

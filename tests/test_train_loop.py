@@ -21,14 +21,15 @@ def _pretrained(tmp_path):
     return root, {k: v.clone() for k, v in m.state_dict().items()}
 
 
-def _run(tmp_path, device, lora, capsys):
+def _run(tmp_path, device, lora, capsys, fused_adamw=False):
     from t2v_b200 import train
     from t2v_b200.models.unet_3d_condition import UNet3DConditionModel
     root, before = _pretrained(tmp_path)
     out = str(tmp_path / ("out_lora" if lora else "out_full"))
     kw = dict(pretrained_model_path=root, output_dir=out, dataset_types=["synthetic"],
               train_data=dict(n=4, n_sample_frames=2, height=64, width=64), max_train_steps=2, learning_rate=1e-3,
-              checkpointing_steps=1, seed=0, shuffle=False, device=device, eval_train=True, max_grad_norm=1.0)
+              checkpointing_steps=1, seed=0, shuffle=False, device=device, eval_train=True, max_grad_norm=1.0,
+              fused_adamw=fused_adamw)
     if lora:
         kw.update(use_unet_lora=True, lora_version="cloneofsimo", lora_rank=4, unet_lora_modules=["UNet3DConditionModel"],
                   trainable_modules=None)
@@ -54,6 +55,12 @@ def _run(tmp_path, device, lora, capsys):
 def test_train_main_cpu_emulated(tmp_path, capsys, lora):
     with emulated_prims():
         _run(tmp_path, "cpu", lora, capsys)
+
+
+@pytest.mark.parametrize("lora", [False, True])
+def test_train_main_cpu_emulated_fused_adamw(tmp_path, capsys, lora):
+    with emulated_prims():
+        _run(tmp_path, "cpu", lora, capsys, fused_adamw=True)
 
 
 @pytest.mark.gpu

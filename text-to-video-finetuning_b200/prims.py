@@ -261,6 +261,16 @@ def dropout_scale_add(x, base, p, scale, seed):
     return out
 
 
+def adamw_step(p, g, m, v, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, zero_grad=False):
+    """Fused AdamW on flat fp32 ranges (p, g, m, v 1-D, same length); shadow: bf16 range of the same length or None."""
+    _chk_f32(p, g, m, v)
+    _chk_bf16(shadow)
+    n = p.numel()
+    assert g.numel() == n and m.numel() == n and v.numel() == n and (shadow is None or shadow.numel() == n)
+    native.check(native.lib().t2v_adamw_step(_p(p), _p(g), _p(m), _p(v), _p(shadow), n, float(lr), float(beta1), float(beta2), float(eps),
+                                             float(weight_decay), int(step), float(grad_scale), int(bool(zero_grad)), _stream()))
+
+
 def add_f32(a, b):
     _chk_f32(a, b)
     out = torch.empty_like(a)

@@ -221,7 +221,14 @@ def main(
 
     abar = ddpm_alphas_cumprod(device=dev)
     stepper = DataParallelStep(unet, abar, passes=2, use_graph=False)  # parameters now live in the flat arena
-    optimizer = torch.optim.AdamW(groups, lr=learning_rate, betas=(adam_beta1, adam_beta2), weight_decay=adam_weight_decay, eps=adam_epsilon)
+    fused_adamw = bool(kwargs.get("fused_adamw", False))   # opt-in: optim.FusedAdamW on the flat arena
+    if fused_adamw:
+        from .optim import FusedAdamW
+        optimizer = FusedAdamW(stepper.arena, groups, lr=learning_rate, betas=(adam_beta1, adam_beta2), weight_decay=adam_weight_decay,
+                               eps=adam_epsilon)
+    else:
+        optimizer = torch.optim.AdamW(groups, lr=learning_rate, betas=(adam_beta1, adam_beta2), weight_decay=adam_weight_decay,
+                                      eps=adam_epsilon)
     sched = torch.optim.lr_scheduler.LambdaLR(optimizer, _lr_lambda(lr_scheduler, lr_warmup_steps * gradient_accumulation_steps,
                                                                     max_train_steps * gradient_accumulation_steps))
 
@@ -255,9 +262,12 @@ def main(
             micro += 1
             if micro % gradient_accumulation_steps:
                 continue  # gradients keep accumulating in the flat buffer
-            if max_grad_norm is not None:
-                torch.nn.utils.clip_grad_norm_([p for g in optimizer.param_groups for p in g["params"]], max_grad_norm)
-            optimizer.step()
+            if fused_adamw:   # clipping is folded into the update as a gradient scale
+                optimizer.step(grad_scale=optimizer.clip_scale(max_grad_norm) if max_grad_norm is not None else 1.0)
+            else:
+                if max_grad_norm is not None:
+                    torch.nn.utils.clip_grad_norm_([p for g in optimizer.param_groups for p in g["params"]], max_grad_norm)
+                optimizer.step()
             sched.step()
             global_step += 1
             if rank == 0 and (global_step % 10 == 0 or global_step == 1):
