@@ -457,6 +457,12 @@ __global__ void ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bf
 }
 
 // Blocks that can be resident at once (the spin barrier needs the whole grid on the chip).
+// Why the barrier cannot deadlock although other kernels may share the SMs: the grid never exceeds what fits on the chip by
+// itself; kernels launched BEFORE this one on any stream terminate without waiting for it, so their SM resources free up and
+// the remaining blocks become resident; kernels launched AFTER it on the same stream (programmatic dependent launch) can
+// only start once every block of this grid has executed griddepcontrol.launch_dependents, i.e. is already resident; and a
+// concurrent kernel on the side stream (weight gradients) never waits on this one either.  The spin is bounded (3 s, then
+// trap) so that a violated assumption fails loudly instead of hanging the GPU.
 static int gn_resident_blocks() {
     static int cached = 0;
     if (cached) return cached;
