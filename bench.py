@@ -27,6 +27,9 @@ CFG2 = dict(model="text-to-video-ms-1.7b UNet3DConditionModel (random init, conv
             text_len=77, text_dim=1024)
 FWD_TFLOP_PER_CLIP = 4.887      # algorithmic 2*MAC of conv/linear/attention contractions, cfg 2
 PASS_TFLOP_PER_CLIP = 14.66     # forward + backward (dgrad + wgrad), full fine-tune
+# of which the spatial self / cross attention products (12 L^2 C per frame and layer fwd+bwd, 12 Lq Lk C for cross attention):
+# 0.367 + 0.043 TFLOP.  They leave gemm_tc_kernel when the fused attention kernels are switched on (T2V_FLASH_ATTN=1).
+ATTN_TFLOP_PER_CLIP = 0.41
 
 
 def peaks():
@@ -273,7 +276,9 @@ def main():
             n_gemm += cnt
         torch.cuda.empty_cache()
         peak_tf, peak_hbm, how = peaks()
-        flops = (PASS_TFLOP_PER_CLIP if not args.small else float("nan")) * B
+        from t2v_b200 import ops as _ops
+        gemm_tflop = PASS_TFLOP_PER_CLIP - (ATTN_TFLOP_PER_CLIP if _ops._Flash.enabled else 0.0)
+        flops = (gemm_tflop if not args.small else float("nan")) * B
         ach = flops / (gemm_ms / 1e3) if gemm_ms > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM conv / linear / attention products)",
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": gemm_traffic(),
