@@ -171,7 +171,11 @@ int t2v_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 /* nn.Dropout fused with the LoRA branch / TemporalConvLayer stage: out = base + scale * x * mask / (1 - p), mask drawn
  * from a stateless counter-based generator keyed by (seed, element index); calling it again with the same seed on dy
  * (base NULL) is the backward.  (reference utils/lora.py:57-62 dropout after lora_up; TemporalConvLayer Dropout(0.1))    */
-int t2v_dropout_scale_add(const void* x, const void* base, void* out, int64_t n, float p, float scale, uint64_t seed, void* stream);
+int t2v_dropout_scale_add(const void* x, const void* base, void* out, int64_t n, float p, float scale, uint64_t seed, const int64_t* epoch,
+                          void* stream);
+/* *counter += value on the device (the per-step dropout epoch: `epoch` above may be NULL or point at such a counter, whose
+ * value is mixed into the seed when the kernel RUNS, so a replayed CUDA graph draws new masks every step).              */
+int t2v_counter_add(int64_t* counter, int64_t value, void* stream);
 
 /* Upsample2D's F.interpolate(mode="nearest") on [N][H][W][C] and its gradient (any size ratio).                      */
 int t2v_upsample_nearest_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t Ho, int32_t Wo, int32_t C, void* stream);
@@ -203,11 +207,19 @@ int t2v_attn_small_bwd(const void* q, const void* k, const void* v, const void* 
                        int32_t inner, int64_t outer_rows, int64_t inner_rows, int64_t seq_rows, int64_t ld_in, int64_t ld_out,
                        int32_t heads, int32_t L, int32_t D, void* stream);
 
-/* Fused AdamW over n contiguous fp32 parameters of the flat arena (torch.optim.AdamW semantics, the optimizer the reference
- * builds at train.py:616-623): updates p, m, v in place from g * grad_scale, optionally writes the bf16 compute copy of p
- * (shadow_bf16, may be NULL) and zeroes g (zero_grad != 0).  step counts optimizer steps from 1 (bias correction).        */
-int t2v_adamw_step(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1, float beta2, float eps,
-                   float weight_decay, int32_t step, float grad_scale, int32_t zero_grad, void* stream);
+/* Fused AdamW + global-norm clipping on the flat arena (torch.optim.AdamW semantics; reference train.py:616-623, clipping
+ * :868-876).  The trainable set is a chunk table of int64 (offset, length) pairs into the flat fp32 buffers (multiples of 64
+ * elements).  All step-dependent scalars live in device memory so the three launches can be captured in a CUDA graph:
+ *   t2v_sqnorm_chunks   *out += sum g^2 over the chunks (fp64)
+ *   t2v_adamw_prepare   state[0] (int64 step count) += 1; for each of n_sets hyper-parameter rows hp_in[s] = (lr, beta1, beta2,
+ *                       eps, weight_decay) writes hp[s] = (.., bias_c1, sqrt(bias_c2), clip factor); the clip factor is
+ *                       min(1, max_norm / (sqrt(sq[0]) + 1e-6)) (1 when max_norm <= 0); sq[1] = norm, sq[0] = 0
+ *   t2v_adamw_chunks    updates p, m, v from g * clip, writes the bf16 compute copy of p for offsets < n_shadow (shadow may be
+ *                       NULL) and zeroes g when zero_grad != 0.  hp points at ONE 8-float row.                           */
+int t2v_sqnorm_chunks(const float* g, const int64_t* chunks, int32_t n_chunks, double* out, void* stream);
+int t2v_adamw_prepare(const float* hp_in, float* hp, int32_t n_sets, int64_t* state, double* sq, float max_norm, void* stream);
+int t2v_adamw_chunks(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_t n_shadow, const int64_t* chunks, int32_t n_chunks,
+                     const float* hp, int32_t zero_grad, void* stream);
 
 #ifdef __cplusplus
 }

@@ -206,7 +206,9 @@ def _mix32(seed, idx):
     return lsr(z ^ lsr(z, 31), 32)
 
 
-def dropout_scale_add(x, base, p, scale, seed):
+def dropout_scale_add(x, base, p, scale, seed, epoch=None):
+    if epoch is not None:   # same mixing as the kernel: seed ^= epoch * 0xD1342543DE82EF95 (mod 2^64)
+        seed = (int(seed) ^ ((int(epoch.item()) * 0xD1342543DE82EF95) & 0xFFFFFFFFFFFFFFFF)) & 0xFFFFFFFFFFFFFFFF
     idx = torch.arange(x.numel(), dtype=torch.int64, device=x.device)
     keep = (_mix32(seed, idx) >= int(float(p) * 4294967296.0)).view(x.shape)
     k = torch.tensor(scale, dtype=torch.float32) / (torch.tensor(1.0, dtype=torch.float32) - torch.tensor(p, dtype=torch.float32))
@@ -216,20 +218,48 @@ def dropout_scale_add(x, base, p, scale, seed):
     return y.to(BF)
 
 
+def counter_add(counter, value=1):
+    counter.add_(value)
+
+
 @torch.no_grad()
-def adamw_step(p, g, m, v, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, zero_grad=False):
-    """torch.optim.AdamW's single-tensor update, on flat ranges (same arithmetic order as the kernel)."""
-    gs = g * grad_scale
-    p.mul_(1.0 - lr * weight_decay)
-    m.mul_(beta1).add_(gs, alpha=1.0 - beta1)
-    v.mul_(beta2).addcmul_(gs, gs, value=1.0 - beta2)
-    bc1 = 1.0 - beta1 ** step
-    bc2_sqrt = (1.0 - beta2 ** step) ** 0.5
-    p.addcdiv_(m, v.sqrt() / bc2_sqrt + eps, value=-(lr / bc1))
-    if shadow is not None:
-        shadow.copy_(p)
-    if zero_grad:
-        g.zero_()
+def sqnorm_chunks(g, chunks, out):
+    for off, n in chunks.tolist():
+        out[0] += g[off:off + n].double().pow(2).sum()
+
+
+@torch.no_grad()
+def adamw_prepare(hp_in, hp, state, sq, max_norm):
+    """csrc/optim.cu adamw_prepare_kernel: step count, bias corrections, clip factor - on the 'device' tensors."""
+    state[0] += 1
+    step = int(state[0])
+    norm = float(sq[0]) ** 0.5
+    sq[1] = norm
+    sq[0] = 0.0
+    scale = min(1.0, max_norm / (norm + 1e-6)) if (max_norm or 0.0) > 0 else 1.0
+    for s in range(hp_in.shape[0]):
+        b1, b2 = float(hp_in[s, 1]), float(hp_in[s, 2])
+        hp[s, :5] = hp_in[s]
+        hp[s, 5] = 1.0 - b1 ** step
+        hp[s, 6] = (1.0 - b2 ** step) ** 0.5
+        hp[s, 7] = scale
+
+
+@torch.no_grad()
+def adamw_chunks(p, g, m, v, shadow, n_shadow, chunks, hp_row, zero_grad=True):
+    """torch.optim.AdamW's single-tensor update on the chunk table (same arithmetic order as the kernel)."""
+    lr, b1, b2, eps, wd, bc1, bc2s, gscale = (float(x) for x in hp_row.tolist())
+    for off, n in chunks.tolist():
+        sl = slice(off, off + n)
+        gs = g[sl] * gscale
+        p[sl].mul_(1.0 - lr * wd)
+        m[sl].mul_(b1).add_(gs, alpha=1.0 - b1)
+        v[sl].mul_(b2).addcmul_(gs, gs, value=1.0 - b2)
+        p[sl].addcdiv_(m[sl], v[sl].sqrt() / bc2s + eps, value=-(lr / bc1))
+        if shadow is not None and off < n_shadow:
+            shadow[sl].copy_(p[sl])
+        if zero_grad:
+            g[sl].zero_()
 
 
 def add_f32(a, b):

@@ -2,18 +2,14 @@
 
 CPU (always): the host logic of the fused path - dispatch, saved tensors, column-sliced fused QKV / K|V operands and
 gradient layouts - over the emulated primitives must reproduce the unfused path exactly.
-GPU (opt-in, T2V_FLASH_ATTN=1, until the path has been through one full GPU suite + bench run): the kernels through the
-C ABI vs the fp32 restatement, and the end-to-end UNet parity of tests/test_unet_gpu.py with the fused path switched on.
-Both passed on B200 at the end of round 1 (profiles/r1_flash_attn_suite.txt, profiles/r1_flash_attn_experiment.txt)."""
-import os
-
+GPU: the kernels through the C ABI vs the fp32 restatement, and the end-to-end UNet parity of tests/test_unet_gpu.py with
+the fused path (the default since round 2) switched on explicitly."""
 import pytest
 import torch
 
 from helpers import emulated_prims, rel_l2
 from oracle import ops_ref
 
-FLASH_ON_GPU = bool(os.environ.get("T2V_FLASH_ATTN"))
 
 
 def _attend(flash, fused, cross, q, k, v, do, heads):
@@ -59,7 +55,6 @@ def test_fused_path_host_logic_matches_unfused_cpu(fused, cross):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not FLASH_ON_GPU, reason="fused attention is opt-in (T2V_FLASH_ATTN=1) until it has been through the GPU suite")
 @pytest.mark.parametrize("Nb,Lq,Lk,heads,fused", [(3, 256, 256, 5, False), (2, 1024, 1024, 5, True), (2, 200, 200, 2, False),
                                                    (1, 64, 64, 1, False), (2, 2304, 77, 5, True), (1, 16384, 77, 5, True)])
 def test_kernels_match_restatement_gpu(Nb, Lq, Lk, heads, fused):
@@ -96,7 +91,6 @@ def test_kernels_match_restatement_gpu(Nb, Lq, Lk, heads, fused):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not FLASH_ON_GPU, reason="fused attention is opt-in (T2V_FLASH_ATTN=1) until it has been through the GPU suite")
 def test_unet_parity_with_fused_attention_gpu():
     import test_unet_gpu as U
     from t2v_b200 import ops

@@ -1,14 +1,11 @@
 """Fused AdamW on the flat arena (optim.FusedAdamW): the update rule (restated in oracle/ops_ref.adamw_step, which the CUDA
 kernel csrc/optim.cu mirrors line by line) against torch.optim.AdamW, with several parameter groups, frozen parameters
 and folded gradient clipping.  CPU always; the GPU variant is opt-in (T2V_TEST_OPTIN=1) until the kernel has run once."""
-import os
-
 import pytest
 import torch
 
 from helpers import emulated_prims
 
-OPTIN = bool(os.environ.get("T2V_TEST_OPTIN"))
 
 
 def _net(device):
@@ -59,6 +56,5 @@ def test_fused_adamw_matches_torch_cpu():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not OPTIN, reason="opt-in (T2V_TEST_OPTIN=1): csrc/optim.cu has not run on a GPU yet")
 def test_fused_adamw_matches_torch_gpu():
     _compare("cuda", 1e-5)

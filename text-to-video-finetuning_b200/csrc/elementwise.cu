@@ -395,8 +395,12 @@ __device__ __forceinline__ uint32_t mix32(uint64_t seed, uint64_t idx) {
     return uint32_t((z ^ (z >> 31)) >> 32);
 }
 __global__ void dropout_scale_add_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ base,
-                                         __nv_bfloat16* __restrict__ out, int64_t nvec, float p, float scale, uint64_t seed) {
+                                         __nv_bfloat16* __restrict__ out, int64_t nvec, float p, float scale, uint64_t seed,
+                                         const int64_t* __restrict__ epoch) {
     pdl_sync();
+    // `epoch` (device memory, bumped once per training step) keeps the masks of a replayed CUDA graph fresh: the host seed
+    // is baked into the captured launch, the epoch is read when the kernel runs
+    if (epoch) seed ^= uint64_t(*epoch) * 0xD1342543DE82EF95ull;
     const uint32_t thresh = uint32_t(double(p) * 4294967296.0);
     const float k = scale / (1.f - p);
     GRID_STRIDE(i, nvec) {
@@ -565,10 +569,11 @@ int t2v_softmax_bwd(const void* p, const float* dp, void* ds, int64_t rows, int3
     launch_pdl(softmax_bwd_kernel, dim3(grid), dim3(256), size_t(0), ST, BF(p), dp, BFW(ds), rows, n_valid, ld_p, ld_dp, scale);
     return launch_checked(int(cudaGetLastError()), "softmax_bwd");
 }
-int t2v_dropout_scale_add(const void* x, const void* base, void* out, int64_t n, float p, float scale, uint64_t seed, void* stream) {
+int t2v_dropout_scale_add(const void* x, const void* base, void* out, int64_t n, float p, float scale, uint64_t seed, const int64_t* epoch,
+                          void* stream) {
     if (n % 8) return fail(-2, "dropout_scale_add: n must be a multiple of 8");
     if (!(p >= 0.f && p < 1.f)) return fail(-2, "dropout_scale_add: p=%f out of range", p);
-    launch_pdl(dropout_scale_add_kernel, dim3(ew_grid(n / 8)), dim3(256), size_t(0), ST, BF(x), BF(base), BFW(out), n / 8, p, scale, seed);
+    launch_pdl(dropout_scale_add_kernel, dim3(ew_grid(n / 8)), dim3(256), size_t(0), ST, BF(x), BF(base), BFW(out), n / 8, p, scale, seed, epoch);
     return launch_checked(int(cudaGetLastError()), "dropout_scale_add");
 }
 int t2v_vae_sample(const void* moments, const float* eps, float* out, int32_t B, int32_t F, int32_t HW, float scale, void* stream) {

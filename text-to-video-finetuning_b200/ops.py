@@ -437,9 +437,9 @@ def _rup8(n):
 
 
 class _Flash:
-    # Fused attention kernels (csrc/flash_attn.cu): kernel and end-to-end UNet parity verified on B200 with the flag on
-    # (profiles/r1_flash_attn_*.txt); opt-in until the full GPU suite and the bench have run with them.
-    enabled = bool(os.environ.get("T2V_FLASH_ATTN"))
+    # Fused attention kernels (csrc/flash_attn.cu) are the default path for head_dim 64 (every attention of the UNet);
+    # T2V_NO_FLASH_ATTN=1 selects the unfused bgemm / softmax / bgemm path (A/B switch, also what other head dims use).
+    enabled = not os.environ.get("T2V_NO_FLASH_ATTN")
 
 
 def _use_flash(q, heads):

@@ -253,22 +253,41 @@ def scale_bf16(a, alpha):
     return out
 
 
-def dropout_scale_add(x, base, p, scale, seed):
-    """base + scale * dropout_p(x); the mask is a pure function of (seed, element index)."""
+def dropout_scale_add(x, base, p, scale, seed, epoch=None):
+    """base + scale * dropout_p(x); the mask is a pure function of (seed, *epoch, element index).  `epoch`: optional int64
+    device counter read when the kernel runs (see counter_add) - it keeps the masks of a replayed CUDA graph fresh."""
     _chk_bf16(x, base)
     out = torch.empty_like(x)
-    native.check(native.lib().t2v_dropout_scale_add(_p(x), _p(base), _p(out), x.numel(), float(p), float(scale), int(seed), _stream()))
+    native.check(native.lib().t2v_dropout_scale_add(_p(x), _p(base), _p(out), x.numel(), float(p), float(scale), int(seed), _p(epoch), _stream()))
     return out
 
 
-def adamw_step(p, g, m, v, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, zero_grad=False):
-    """Fused AdamW on flat fp32 ranges (p, g, m, v 1-D, same length); shadow: bf16 range of the same length or None."""
-    _chk_f32(p, g, m, v)
+def counter_add(counter, value=1):
+    """*counter += value on the device (int64 scalar tensor)."""
+    assert counter.dtype == torch.int64 and counter.is_cuda
+    native.check(native.lib().t2v_counter_add(_p(counter), int(value), _stream()))
+
+
+def sqnorm_chunks(g, chunks, out):
+    """out[0] (fp64) += sum of g^2 over the (offset, length) chunks of the flat fp32 buffer g."""
+    _chk_f32(g)
+    assert chunks.dtype == torch.int64 and out.dtype == torch.float64
+    native.check(native.lib().t2v_sqnorm_chunks(_p(g), _p(chunks), chunks.shape[0], _p(out), _stream()))
+
+
+def adamw_prepare(hp_in, hp, state, sq, max_norm):
+    """Device-side scalars of one optimizer step: step count, bias corrections, clip factor (see include/t2v_b200.h)."""
+    _chk_f32(hp_in, hp)
+    assert state.dtype == torch.int64 and sq.dtype == torch.float64 and hp.shape[0] == hp_in.shape[0]
+    native.check(native.lib().t2v_adamw_prepare(_p(hp_in), _p(hp), hp_in.shape[0], _p(state), _p(sq), float(max_norm or 0.0), _stream()))
+
+
+def adamw_chunks(p, g, m, v, shadow, n_shadow, chunks, hp_row, zero_grad=True):
+    """Fused AdamW over the chunk table of one hyper-parameter set; hp_row: the set's 8 floats on the device."""
+    _chk_f32(p, g, m, v, hp_row)
     _chk_bf16(shadow)
-    n = p.numel()
-    assert g.numel() == n and m.numel() == n and v.numel() == n and (shadow is None or shadow.numel() == n)
-    native.check(native.lib().t2v_adamw_step(_p(p), _p(g), _p(m), _p(v), _p(shadow), n, float(lr), float(beta1), float(beta2), float(eps),
-                                             float(weight_decay), int(step), float(grad_scale), int(bool(zero_grad)), _stream()))
+    native.check(native.lib().t2v_adamw_chunks(_p(p), _p(g), _p(m), _p(v), _p(shadow), int(n_shadow), _p(chunks), chunks.shape[0], _p(hp_row),
+                                               int(bool(zero_grad)), _stream()))
 
 
 def add_f32(a, b):
