@@ -1,16 +1,21 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path named by BASELINE.json: finetune frames/sec of the text-to-video-ms-1.7b UNet
-(16 frames x 256^2 -> latents 1x4x16x32x32, bf16 compute, full fine-tune: forward + backward of one UNet pass per
-step, fp32 gradients, one gradient all-reduce per step when N > 1), data-parallel by clip.
+"""Benchmark of the hot path named by BASELINE.json.
 
-  python bench.py --gpus N --steps K --warmup W            -> one JSON line (rank 0)
-  python bench.py --impl reference ...                     -> the reference algorithm on the host CPU cores
-                                                              (oracle port; the reference's diffusers path cannot be
-                                                              installed here - see DESIGN.md), same metric/unit.
-Everything under oracle/ is used only for the cpu_baseline / --impl reference leg.
+Default workload (configs[1], the one the metric is quoted on): finetune frames/sec of the text-to-video-ms-1.7b UNet,
+16 frames x 256^2 -> latents 1x4x16x32x32 per GPU, bf16 compute, FULL fine-tune.  One step = one UNet forward + backward
+pass (fp32 gradients, TemporalConvLayer dropout live), ONE gradient all-reduce when N > 1, global-norm clipping and the
+fused AdamW update of all 1.41 B parameters - replayed as one CUDA graph; data-parallel by clip (weak scaling).
+
+  python bench.py --gpus N --steps K --warmup W                 -> one JSON line (rank 0)
+  python bench.py --workload lora|zeroscope|vae ...             -> configs[2] / [3] / [4] of BASELINE.json (extra lines)
+  python bench.py --impl reference ...                          -> the reference algorithm on the host CPU cores: the
+        reference's own models/*.py when /root/reference is present (build container), else the oracle port of it (GPU box);
+        its diffusers dependency cannot be installed here, same metric/unit.
+Everything under oracle/ is used only for the parity / cpu_baseline / --impl reference legs.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -23,13 +28,25 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-CFG2 = dict(model="text-to-video-ms-1.7b UNet3DConditionModel (random init, conv4 re-drawn N(0,0.01))", frames=16, latent_hw=(32, 32),
-            text_len=77, text_dim=1024)
-FWD_TFLOP_PER_CLIP = 4.887      # algorithmic 2*MAC of conv/linear/attention contractions, cfg 2
-PASS_TFLOP_PER_CLIP = 14.66     # forward + backward (dgrad + wgrad), full fine-tune
-# of which the spatial self / cross attention products (12 L^2 C per frame and layer fwd+bwd, 12 Lq Lk C for cross attention):
-# 0.367 + 0.043 TFLOP.  They leave gemm_tc_kernel when the fused attention kernels are switched on (T2V_FLASH_ATTN=1).
-ATTN_TFLOP_PER_CLIP = 0.41
+# algorithmic 2*MAC of the conv / linear / attention contractions per clip (validated by the 1,411,233,860-parameter walk)
+WORKLOADS = {
+    "cfg2": dict(name="configs[1]: text-to-video-ms-1.7b full finetune, 16 frames 256x256 (latents 1x4x16x32x32 per GPU), bf16",
+                 model="text-to-video-ms-1.7b UNet3DConditionModel (random init, conv4 re-drawn N(0,0.01))",
+                 frames=16, latent_hw=(32, 32), text_len=77, text_dim=1024, fwd_tflop=4.887, pass_tflop=14.66, attn_tflop=0.41,
+                 lora_rank=0, grad_ckpt=False),
+    "lora": dict(name="configs[2]: text-to-video-ms-1.7b LoRA rank-16 (cloneofsimo, target UNet3DConditionModel), 24 frames 320x576 "
+                      "(latents 1x4x24x40x72 per GPU), bf16",
+                 model="text-to-video-ms-1.7b UNet3DConditionModel + 574 LoRA wrappers (29,246,112 trainable parameters)",
+                 frames=24, latent_hw=(40, 72), text_len=77, text_dim=1024, fwd_tflop=21.395 + 0.79, pass_tflop=2 * (21.395 + 0.79) + 0.79,
+                 attn_tflop=3 * 0.073 * 21.395, lora_rank=16, grad_ckpt=False),
+    "zeroscope": dict(name="configs[3]: zeroscope_v2_576w (same architecture) full finetune, 32 frames 512x512 (latents 1x4x32x64x64 per "
+                           "GPU), bf16, gradient checkpointing",
+                      model="zeroscope_v2_576w UNet3DConditionModel (random init, conv4 re-drawn N(0,0.01))",
+                      frames=32, latent_hw=(64, 64), text_len=77, text_dim=1024, fwd_tflop=41.71, pass_tflop=125.1,
+                      attn_tflop=3 * 0.099 * 41.71, lora_rank=0, grad_ckpt=True),
+}
+CFG2 = WORKLOADS["cfg2"]
+VAE_TFLOP_PER_FRAME = {256: 0.2727, 512: 1.1167, 768: 2.6091}
 
 
 def peaks():
@@ -92,7 +109,10 @@ def synthetic_inputs(batch, cfg, seed, device="cpu", pin=False):
     return [x.to(device) for x in out] if device != "cpu" else out
 
 
-def build_unet(device, small=False):
+def build_unet(device, small=False, dropout=True):
+    """Random-init UNet of the ms-1.7b / zeroscope architecture (no checkpoints offline); TemporalConvLayer.conv4 is
+    re-drawn N(0, 0.01) so the temporal-conv branch carries signal.  Training mode: the TemporalConvLayer
+    dropout (p = 0.1) is live unless dropout=False."""
     from t2v_b200.models.unet_3d_condition import UNet3DConditionModel
     kw = dict(block_out_channels=(128, 256, 320, 320), cross_attention_dim=1024) if small else {}
     torch.manual_seed(1234)
@@ -102,51 +122,72 @@ def build_unet(device, small=False):
         for n, p in m.named_parameters():
             if ".conv4.3." in n:
                 p.normal_(0.0, 0.01)
-    for mod in m.modules():
-        if isinstance(mod, torch.nn.Dropout):
-            mod.p = 0.0  # round 1: dropout-free step (reference eval_train mode, train.py:779-781); stated in config
+    if not dropout:
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
     return m.train()
 
 
-def oracle_pass_seconds(sd_cpu, cfg, frames, threads, reps=1):
-    """One forward+backward of the reference algorithm (oracle port, fp32) on the host CPU."""
+def oracle_pass(sd_cpu, cfg, inputs, threads):
+    """One forward+backward of the reference algorithm (oracle port, fp32) on the host CPU.  Returns seconds, loss, grad norm."""
     from oracle import leaves as L
     from oracle import unet3d_ref as R
     torch.set_num_threads(threads)
-    c = dict(cfg)
-    c["frames"] = frames
-    lat, noise, t, ehs = synthetic_inputs(1, c, 99)
-    p = {k: v.requires_grad_(True) for k, v in sd_cpu.items()}
-    best = None
-    for _ in range(reps):
-        for v in p.values():
-            v.grad = None
-        t0 = time.perf_counter()
-        loss, _ = R.finetune_loss(p, R.full_config(**c.get("unet_kwargs", {})), lat, noise, t, ehs, L.ddpm_alphas_cumprod())
-        loss.backward()
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return best, float(loss)
+    lat, noise, t, ehs = inputs
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in sd_cpu.items()}
+    t0 = time.perf_counter()
+    loss, _ = R.finetune_loss(p, R.full_config(**cfg.get("unet_kwargs", {})), lat, noise, t, ehs, L.ddpm_alphas_cumprod())
+    loss.backward()
+    dt = time.perf_counter() - t0
+    gn = math.sqrt(sum(float(v.grad.double().pow(2).sum()) for v in p.values() if v.grad is not None))
+    return dt, float(loss), gn
+
+
+def reference_pass(Ref, sd_cpu, cfg, inputs, threads):
+    """The same pass through the reference's UNMODIFIED models/unet_3d_condition.py + unet_3d_blocks.py (imported from
+    /root/reference over the diffusers stand-in, oracle/reference_import.py) with the step glue of train.py:751-834."""
+    from oracle import leaves as L
+    torch.set_num_threads(threads)
+    lat, noise, t, ehs = inputs
+    m = Ref(**cfg.get("unet_kwargs", {}))
+    m.load_state_dict(sd_cpu)
+    m.train()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    t0 = time.perf_counter()
+    noisy = L.add_noise(lat, noise, t, L.ddpm_alphas_cumprod())
+    pred = m(noisy, t, encoder_hidden_states=ehs).sample
+    loss = torch.nn.functional.mse_loss(pred.float(), noise.float(), reduction="mean")
+    loss.backward()
+    dt = time.perf_counter() - t0
+    gn = math.sqrt(sum(float(p.grad.double().pow(2).sum()) for p in m.parameters() if p.grad is not None))
+    return dt, float(loss), gn
 
 
 def gemm_traffic():
     """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum averaged over the
-    launches of one step) from the committed ncu capture profiles/r1_gemm_traffic.json; None if the file is absent."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")) as f:
-            return float(json.load(f)["dram_bytes_per_launch"])
-    except (OSError, KeyError, ValueError):
-        return None
+    launches of one step) from the committed ncu capture; None if the file is absent."""
+    for name in ("r2_gemm_traffic.json", "r1_gemm_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return float(json.load(f)["dram_bytes_per_launch"])
+        except (OSError, KeyError, ValueError):
+            continue
+    return None
 
 
 def run_reference(args):
-    """--impl reference: the reference algorithm (oracle port of train.py:739-834 + UNet wiring) on host cores."""
+    """--impl reference: the reference algorithm on the host cores, full workload shape (16-frame clip), bounded by steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle.reference_import import import_reference_unet, reference_available
     from t2v_b200.models.unet_3d_condition import UNet3DConditionModel  # parameter shapes only (random init)
-    threads = min(os.cpu_count() or 1, 32)  # the oracle's small fp32 ops do not scale past ~32 threads
-    cfg = dict(CFG2)
+    wl = WORKLOADS[args.workload if args.workload in WORKLOADS else "cfg2"]
+    threads = min(os.cpu_count() or 1, 32)  # the small fp32 ops of this model do not scale past ~32 threads
+    cfg = dict(wl)
     kw = dict(block_out_channels=(128, 256, 320, 320)) if args.small else {}
     cfg["unet_kwargs"] = kw
     torch.manual_seed(1234)
@@ -155,20 +196,29 @@ def run_reference(args):
     for k in sd:
         if ".conv4.3." in k:
             sd[k].normal_(0.0, 0.01)
-    frames = args.ref_frames
+    del m
+    frames = args.ref_frames or wl["frames"]
+    c = dict(cfg)
+    c["frames"] = frames
+    inputs = synthetic_inputs(1, c, 99)
+    Ref = import_reference_unet() if reference_available() else None
+    kind = "reference" if Ref is not None else "port"
     times = []
     for i in range(args.warmup + args.steps):
-        dt, _ = oracle_pass_seconds(sd, cfg, frames, threads)
+        dt = (reference_pass(Ref, sd, cfg, inputs, threads) if Ref is not None else oracle_pass(sd, cfg, inputs, threads))[0]
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * sum(times) / len(times)
     fps = frames / (ms / 1e3)
+    what = ("the reference's unmodified models/*.py over the diffusers stand-in" if Ref is not None else
+            "oracle port of the reference algorithm (/root/reference is absent on this box)")
     line = {"impl": "reference", "metric": "finetune frames/sec (one UNet fwd+bwd pass per step)", "value": fps, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: ms-1.7b full finetune 16f 256^2, one pass", "sample": f"{frames}-frame clip at 32x32 latents"},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                             "sample": f"{len(times)} fwd+bwd passes of a {frames}-frame clip (oracle port of the reference algorithm, fp32)"},
+            "config": {"workload": wl["name"], "sample": f"{frames}-frame clip, fwd+bwd only (no optimizer step on the CPU arm)",
+                       "same_config": frames == wl["frames"]},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
+                             "sample": f"{len(times)} fwd+bwd passes of a {frames}-frame clip, {what}, fp32, {threads} threads"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -200,7 +250,7 @@ def shutdown(world, step=None):
     if world <= 1:
         return
     import gc
-    import threading
+    import torch.distributed as dist
     sys.stdout.flush()
     sys.stderr.flush()
     threading.Timer(20.0, lambda: os._exit(0)).start()
@@ -215,75 +265,191 @@ def shutdown(world, step=None):
         os._exit(0)
 
 
+def time_events(fn, n):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def run_vae(args, dev):
+    """configs[4]: AutoencoderKL.encode throughput (tensor_to_vae_latent, train.py:339-347) at 256 / 512 / 768 px, frames
+    batched, full SD-VAE encoder widths (128-256-512-512), random init."""
+    from t2v_b200 import native
+    from t2v_b200.vae import AutoencoderKL, tensor_to_vae_latent
+    native.lib()
+    torch.manual_seed(7)
+    with torch.device(dev):
+        vae = AutoencoderKL()
+    vae = vae.eval()
+    peak_tf, _, how = peaks()
+    sweep = {}
+    for res, frames in ((256, 16), (512, 16), (768, 8)):
+        host = (torch.rand(1, frames, 3, res, res) * 2 - 1).pin_memory()
+        x = host.to(dev)
+        for _ in range(max(args.warmup, 3)):
+            tensor_to_vae_latent(x, vae)
+        torch.cuda.synchronize()
+        n0 = native.launch_count()
+        ms = time_events(lambda: tensor_to_vae_latent(x, vae), args.steps)
+        launches = (native.launch_count() - n0) // args.steps
+        ms_e2e = time_events(lambda: tensor_to_vae_latent(host.to(dev, non_blocking=True), vae).float().mean().item(), args.steps)
+        tf = VAE_TFLOP_PER_FRAME[res] * frames
+        sweep[str(res)] = {"frames_per_batch": frames, "ms_per_batch": ms, "frames_per_s": frames / (ms / 1e3),
+                           "e2e_frames_per_s": frames / (ms_e2e / 1e3), "tflops": tf / (ms / 1e3), "frac_of_peak": tf / (ms / 1e3) / peak_tf,
+                           "launches_per_batch": int(launches), "h2d_bytes": host.numel() * 4}
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import leaves as L
+        threads = min(os.cpu_count() or 1, 32)
+        torch.set_num_threads(threads)
+        sd = {k: v.detach().float().cpu() for k, v in vae.state_dict().items()}
+        xc = torch.rand(2, 3, 256, 256) * 2 - 1
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            L.vae_encode_moments(sd, xc)
+        dt = time.perf_counter() - t0
+        cpu = {"value": 2 / dt, "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": f"2 frames at 256x256, oracle port of AutoencoderKL.encode, fp32, {threads} threads"}
+    main_res = sweep["256"]
+    emit({"metric": "AutoencoderKL.encode frames/sec (256x256 frames, batch of 16)", "value": main_res["frames_per_s"], "unit": "frames/s",
+          "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": main_res["ms_per_batch"], "higher_is_better": True,
+          "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+          "config": {"workload": "configs[4]: AutoencoderKL.encode throughput sweep, batched frames at 256/512/768, 1xB200",
+                     "l2": "activations of a 16-frame batch (>= 268 MB at the first level) exceed the 126 MB L2"},
+          "sweep": sweep, "e2e": {"value": main_res["e2e_frames_per_s"], "unit": "frames/s", "h2d_bytes_per_step": main_res["h2d_bytes"],
+                                  "d2h_bytes_per_step": 4},
+          "gpu_launches": int(main_res["launches_per_batch"] * args.steps),
+          "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (3x3 implicit-GEMM convolutions, 98 % of the encoder FLOPs)",
+                       "achieved": main_res["tflops"], "peak": peak_tf, "unit": "TFLOP/s", "frac": main_res["frac_of_peak"], "traffic": None,
+                       "note": "whole-encode FLOPs over whole-encode time (not per-kernel)", "peak_source": how},
+          "cpu_baseline": cpu})
+
+
 def main():
     quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "lora", "zeroscope", "vae"])
     ap.add_argument("--small", action="store_true", help="debug-size UNet (not a valid bench line)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
-    ap.add_argument("--ref-frames", type=int, default=4, help="frames of the bounded CPU sample (reference arm)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-optimizer", action="store_true", help="forward + backward (+ all-reduce) only - NOT a valid finetune step")
+    ap.add_argument("--no-dropout", action="store_true")
+    ap.add_argument("--ref-frames", type=int, default=0, help="frames of the CPU clip (reference arm / cpu_baseline); 0 = the workload's")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (and with it the parity check)")
+    ap.add_argument("--no-roofline", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.steps is None:
+        args.steps = 20 if world == 1 else 50   # collective-bound timings need more samples (round-1 verdict)
     if args.impl == "reference":
+        args.steps = min(args.steps, 3)
+        args.warmup = min(args.warmup, 1)
         return run_reference(args)
+    args.warmup = max(args.warmup, 3)
 
     import torch.distributed as dist
     from t2v_b200 import native
     from t2v_b200 import step as S
+    from t2v_b200.optim import FusedAdamW
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if args.workload == "vae":
+        if rank == 0:
+            run_vae(args, dev)
+        return
+    wl = WORKLOADS[args.workload]
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     native.lib()  # fail loudly if the CUDA extension is missing
 
-    unet = build_unet(dev, args.small)
+    unet = build_unet(dev, args.small, dropout=not args.no_dropout)
+    if wl["lora_rank"]:
+        from t2v_b200.utils.lora_handler import LoraHandler
+        unet.requires_grad_(False)
+        handler = LoraHandler(version="cloneofsimo", use_unet_lora=True, unet_replace_modules=["UNet3DConditionModel"])
+        torch.manual_seed(4321)   # rank-independent LoRA initialisation
+        handler.add_lora_to_model(True, unet, handler.unet_replace_modules, 0.1, "", r=wl["lora_rank"])
+        unet = unet.to(dev).train()
+        with torch.no_grad():     # lora_up starts at zero (reference utils/lora.py:54-55): give the branch signal for the bench
+            for n, p in unet.named_parameters():
+                if "lora_up" in n:
+                    p.normal_(0.0, 0.01)
+    unet._set_gradient_checkpointing(bool(wl["grad_ckpt"]))
     abar = S.ddpm_alphas_cumprod(device=dev)
     step = S.DataParallelStep(unet, abar, passes=1, use_graph=not args.no_graph)
+    optimizer = None
+    trainable = [p for p in unet.parameters() if p.requires_grad]
+    n_trainable = sum(p.numel() for p in trainable)
+    if not args.no_optimizer:
+        # the reference's optimizer settings (configs/v2/train_config.yaml: lr 5e-6, wd 1e-2, max_grad_norm 1.0)
+        optimizer = FusedAdamW(step.arena, [dict(params=trainable)], lr=5e-6, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
+                               max_grad_norm=1.0)
+        step.attach_optimizer(optimizer)
     B = 1
-    host = synthetic_inputs(B, CFG2, 1234 + rank, pin=True)
+    host = synthetic_inputs(B, wl, 1234 + rank, pin=True)
     devin = [x.to(dev) for x in host]
-    frames_per_step = world * B * CFG2["frames"]
+    frames_per_step = world * B * wl["frames"]
 
-    # launches per step, counted on an eager step
+    # ---- parity step (rank 0, N = 1): one eager fwd+bwd at the FULL benchmark size with dropout off, on the initial
+    # weights; loss and global gradient norm are compared with the CPU oracle after the timed region (cpu_baseline leg)
     eager = S.DataParallelStep(unet, abar, passes=1, use_graph=False, adopt=False)
     eager.arena = step.arena
     eager.sync_gradients = False  # profiling passes below run on their own rank: no collective
+    parity_gpu = None
+    do_parity = rank == 0 and world == 1 and not args.no_cpu_baseline and not wl["lora_rank"]
+    if do_parity:
+        sd_cpu = {k: v.detach().float().cpu().contiguous() for k, v in unet.state_dict().items()}
+        unet.eval()
+        lossv = eager(*devin)
+        gn = float(step.arena.grad.double().norm())
+        parity_gpu = (float(lossv), gn)
+        unet.train()
+    # ---- launches per step, counted on an eager step (training mode: dropout kernels included)
     n0 = native.launch_count()
     eager(*devin)
     torch.cuda.synchronize()
     launches_per_step = native.launch_count() - n0
+    if optimizer is not None:   # clip: one sqnorm per hyper-parameter set; one prepare; one update per set
+        launches_per_step += 2 * len(optimizer._sets) + 1
 
     # ---- dominant-kernel roofline: every tensor-core (implicit-GEMM) launch of the step, timed on the device.  One eager
-    # step records each launch's argument template; each distinct template is then replayed as a CUDA graph of
-    # back-to-back launches between CUDA events (eager per-launch events would count host launch gaps as kernel time).
+    # step records each launch's argument template; each distinct template is then replayed as a CUDA graph of back-to-back
+    # launches over ROTATING operand copies (> L2 in total, so no launch finds its operands cached by the previous one)
+    # between CUDA events (eager per-launch events would count host launch gaps as kernel time).
     roof = None
-    if rank == 0:  # before the step graph is captured (graph-pool memory would distort eager allocation)
+    if rank == 0 and not args.no_roofline:  # before the step graph is captured (graph-pool memory would distort eager allocation)
         from t2v_b200 import profiling
         calls = profiling.record_calls(lambda: eager(*devin), ["conv_fwd", "conv_dgrad", "conv_wgrad", "bgemm"])
-        gemm_ms, n_gemm = 0.0, 0
+        gemm_ms, gemm_ms_warm, n_gemm = 0.0, 0.0, 0
         for key, (cnt, _) in calls.items():
-            gemm_ms += profiling.replay_us(key, dev, reps=5) * cnt / 1e3
+            gemm_ms += profiling.replay_us(key, dev, reps=8, cold=True) * cnt / 1e3
+            gemm_ms_warm += profiling.replay_us(key, dev, reps=5, cold=False) * cnt / 1e3
             n_gemm += cnt
         torch.cuda.empty_cache()
         peak_tf, peak_hbm, how = peaks()
         from t2v_b200 import ops as _ops
-        gemm_tflop = PASS_TFLOP_PER_CLIP - (ATTN_TFLOP_PER_CLIP if _ops._Flash.enabled else 0.0)
+        gemm_tflop = wl["pass_tflop"] - (wl["attn_tflop"] if _ops._Flash.enabled else 0.0)
         flops = (gemm_tflop if not args.small else float("nan")) * B
         ach = flops / (gemm_ms / 1e3) if gemm_ms > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM conv / linear / attention products)",
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM conv / linear contractions)",
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": gemm_traffic(),
                 "launches": n_gemm, "distinct_shapes": len(calls), "kernel_ms_per_step": gemm_ms, "share_of_step": None,
-                "algorithmic_tflop_per_step": flops, "peak_source": how}
+                "algorithmic_tflop_per_step": flops, "peak_source": how,
+                "timing": "per-shape CUDA-graph replay over rotating operand copies (L2-cold), CUDA events",
+                "l2_warm": {"kernel_ms_per_step": gemm_ms_warm, "frac": (flops / (gemm_ms_warm / 1e3) / peak_tf) if gemm_ms_warm else None}}
+    step.arena.zero_grads()   # the eager passes above accumulated gradients; the timed steps start from a zero buffer
 
     def barrier():
         if world > 1:
@@ -313,6 +479,14 @@ def main():
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1) / args.steps
+    # ---- the optimizer's share (clip + AdamW over the trainable set), timed alone on the device
+    opt_ms = None
+    if optimizer is not None:
+        optimizer.push_hyperparams()
+        for _ in range(2):
+            optimizer.launch()
+        torch.cuda.synchronize()
+        opt_ms = time_events(optimizer.launch, 5)
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -322,32 +496,55 @@ def main():
         shutdown(world, step)
         return
 
-    cpu = None
+    cpu, parity = None, None
     if not args.no_cpu_baseline and world == 1:
         threads = min(os.cpu_count() or 1, 32)  # more threads only oversubscribe the small fp32 ops of this model
-        sd_cpu = {k: v.detach().float().cpu().contiguous() for k, v in unet.state_dict().items()}
-        cfg = dict(CFG2)
+        cfg = dict(wl)
         cfg["unet_kwargs"] = dict(block_out_channels=(128, 256, 320, 320)) if args.small else {}
-        fr = args.ref_frames
-        dt, _ = oracle_pass_seconds(sd_cpu, cfg, fr, threads)
+        if do_parity:
+            fr = wl["frames"]
+            dt, loss_ref, gn_ref = oracle_pass(sd_cpu, cfg, [x.clone() for x in host], threads)
+            loss_rel = abs(parity_gpu[0] - loss_ref) / abs(loss_ref)
+            gn_rel = abs(parity_gpu[1] - gn_ref) / gn_ref
+            parity = {"loss": parity_gpu[0], "loss_oracle": loss_ref, "loss_rel": loss_rel, "grad_norm": parity_gpu[1],
+                      "grad_norm_oracle": gn_ref, "grad_norm_rel": gn_rel, "tolerance": {"loss_rel": 1e-3, "grad_norm_rel": 5e-3},
+                      "status": "green" if (loss_rel <= 1e-3 and gn_rel <= 5e-3) else "red",
+                      "what": "full benchmark configuration (1.41 B parameters, 16 frames, 32x32 latents), dropout off, same weights and "
+                              "inputs; bf16 kernels vs the fp32 CPU oracle"}
+        else:
+            fr = args.ref_frames or 4
+            c = dict(cfg)
+            c["frames"] = fr
+            import re
+            sd1 = {re.sub(r"\.(linear|conv)\.(weight|bias)$", r".\2", k) if wl["lora_rank"] else k: v.detach().float().cpu().contiguous()
+                   for k, v in unet.state_dict().items() if "lora" not in k}   # base weights only (the CPU arm has no LoRA branch)
+            dt = oracle_pass(sd1, cfg, synthetic_inputs(1, c, 99), threads)[0]
         cpu = {"value": fr / dt, "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": f"one fwd+bwd pass of a {fr}-frame clip at 32x32 latents, oracle port of the reference algorithm, fp32, {threads} threads"}
+               "sample": f"one fwd+bwd pass of a {fr}-frame clip at {wl['latent_hw'][0]}x{wl['latent_hw'][1]} latents, oracle port of the "
+                         f"reference algorithm, fp32, {threads} threads (no optimizer step)"}
 
     in_bytes = sum(x.numel() * x.element_size() for x in host)
     line = {
-        "metric": "finetune frames/sec (one UNet fwd+bwd pass per step)", "value": frames_per_step / (ms / 1e3), "unit": "frames/s",
+        "metric": "finetune frames/sec (one UNet fwd+bwd pass + optimizer step per step)" if optimizer is not None
+        else "fwd+bwd frames/sec (NO optimizer step - not a finetune step)",
+        "value": frames_per_step / (ms / 1e3), "unit": "frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "configs[1]: text-to-video-ms-1.7b full finetune, 16 frames 256x256 (latents 1x4x16x32x32 per GPU), bf16",
-                   "passes_per_step": 1, "global_batch_clips": world * B, "parallelism": f"dp{world}", "dropout": "off (eval_train)",
+        "config": {"workload": wl["name"], "model": wl["model"], "passes_per_step": 1, "global_batch_clips": world * B,
+                   "parallelism": f"dp{world}", "dropout": "off" if args.no_dropout else "on (TemporalConvLayer p=0.1, LoRA p=0.1)",
+                   "optimizer": None if optimizer is None else "fused AdamW + global-norm clip (max_grad_norm 1.0) inside the timed step",
+                   "trainable_parameters": int(n_trainable), "gradient_checkpointing": bool(wl["grad_ckpt"]),
                    "l2": "working set (2.8 GB bf16 weights + activations) >> 126 MB L2; no flush needed",
                    "launch_mode": "eager" if args.no_graph else "cuda-graph replay", "small_debug_model": bool(args.small)},
         "e2e": {"value": frames_per_step / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e},
         "gpu_launches": int(launches_per_step * (args.steps)),
         "launches_per_step": int(launches_per_step),
+        "optimizer_ms": opt_ms,
+        "fwd_bwd_ms": (ms - opt_ms) if opt_ms is not None else ms,
         "clocks": clocks.summary(),
         "loss": lv,
+        "parity": parity,
         "roofline": dict(roof, share_of_step=(roof["kernel_ms_per_step"] / ms)) if roof else None,
         "cpu_baseline": cpu,
     }

@@ -24,7 +24,8 @@ def _compare(device, rtol):
     groups = lambda m: [dict(params=[p for n, p in m.named_parameters() if n.startswith("0.")], lr=3e-3),  # noqa: E731
                         dict(params=[p for n, p in m.named_parameters() if not n.startswith("0.")], lr=1e-3, weight_decay=0.05)]
     o_ref = torch.optim.AdamW(groups(ref), lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-2)
-    o_fus = optim.FusedAdamW(arena, groups(fused), lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-2)
+    o_fus = optim.FusedAdamW(arena, groups(fused), lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-2, max_grad_norm=1.0)
+    assert len(o_fus._sets) == 2 and o_fus.covers_all_trainable()
     g = torch.Generator().manual_seed(1)
     frozen_before = fused[1].weight.detach().clone()
     for step in range(4):
@@ -36,10 +37,10 @@ def _compare(device, rtol):
             grad = torch.randn(p.shape, generator=g).to(device) * (3.0 if step == 2 else 0.3)
             p.grad = grad.clone()
             q.grad.copy_(grad)
-        scale = o_fus.clip_scale(1.0)
-        torch.nn.utils.clip_grad_norm_([p for p in ref.parameters() if p.grad is not None], 1.0)
+        norm = torch.nn.utils.clip_grad_norm_([p for p in ref.parameters() if p.grad is not None], 1.0)
         o_ref.step()
-        o_fus.step(grad_scale=scale, zero_grad=True)
+        o_fus.step(zero_grad=True)     # clip factor, step count and bias corrections are computed on the device
+        assert abs(float(o_fus.last_grad_norm()) - float(norm)) < 1e-5 * float(norm) and o_fus.steps == step + 1
         assert float(arena.grad.abs().max()) == 0.0 or all(float(q.grad.abs().max()) == 0.0 for q in fused.parameters() if q.requires_grad)
     for (n, p), (_, q) in zip(ref.named_parameters(), fused.named_parameters()):
         assert torch.allclose(p, q, rtol=rtol, atol=1e-7), (n, float((p - q).abs().max()))

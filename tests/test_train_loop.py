@@ -21,7 +21,7 @@ def _pretrained(tmp_path):
     return root, {k: v.clone() for k, v in m.state_dict().items()}
 
 
-def _run(tmp_path, device, lora, capsys, fused_adamw=False):
+def _run(tmp_path, device, lora, capsys, fused_adamw=True, **extra):
     from t2v_b200 import train
     from t2v_b200.models.unet_3d_condition import UNet3DConditionModel
     root, before = _pretrained(tmp_path)
@@ -30,12 +30,13 @@ def _run(tmp_path, device, lora, capsys, fused_adamw=False):
               train_data=dict(n=4, n_sample_frames=2, height=64, width=64), max_train_steps=2, learning_rate=1e-3,
               checkpointing_steps=1, seed=0, shuffle=False, device=device, eval_train=True, max_grad_norm=1.0,
               fused_adamw=fused_adamw)
+    kw.update(extra)
     if lora:
         kw.update(use_unet_lora=True, lora_version="cloneofsimo", lora_rank=4, unet_lora_modules=["UNet3DConditionModel"],
                   trainable_modules=None)
     else:
         kw.update(trainable_modules=["attn1", "attn2"])
-    train.main(**kw)
+    result = train.main(**kw)
     log = capsys.readouterr().out
     losses = [float(ln.split("loss")[1].split()[0]) for ln in log.splitlines() if ln.startswith("step ")]
     assert losses and all(math.isfinite(v) for v in losses), log
@@ -49,6 +50,7 @@ def _run(tmp_path, device, lora, capsys, fused_adamw=False):
         moved = [k for k in before if not torch.equal(before[k], after[k])]
         assert moved and all(("attn1" in k or "attn2" in k) for k in moved), moved[:5]
         assert os.path.isdir(os.path.join(out, "checkpoint-1", "unet"))
+    return result
 
 
 @pytest.mark.parametrize("lora", [False, True])
@@ -58,12 +60,25 @@ def test_train_main_cpu_emulated(tmp_path, capsys, lora):
 
 
 @pytest.mark.parametrize("lora", [False, True])
-def test_train_main_cpu_emulated_fused_adamw(tmp_path, capsys, lora):
+def test_train_main_cpu_emulated_torch_adamw(tmp_path, capsys, lora):
     with emulated_prims():
-        _run(tmp_path, "cpu", lora, capsys, fused_adamw=True)
+        _run(tmp_path, "cpu", lora, capsys, fused_adamw=False)
+
+
+def test_train_main_cpu_gradient_accumulation(tmp_path, capsys):
+    with emulated_prims():
+        r = _run(tmp_path, "cpu", False, capsys, gradient_accumulation_steps=2)
+    assert r["steps"] == 2 and r["optimizer"].steps == 2 and r["stepper"]._micro == 4
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("lora", [False, True])
 def test_train_main_gpu(tmp_path, capsys, lora):
-    _run(tmp_path, "cuda:0", lora, capsys)
+    """Default configuration on the GPU: the whole step (two passes, clip + fused AdamW) replayed as one CUDA graph."""
+    r = _run(tmp_path, "cuda:0", lora, capsys)
+    assert r["stepper"].use_graph and len(r["stepper"]._graphs) == 1
+
+
+@pytest.mark.gpu
+def test_train_main_gpu_eager_torch_adamw(tmp_path, capsys):
+    _run(tmp_path, "cuda:0", False, capsys, fused_adamw=False, use_cuda_graph=False)

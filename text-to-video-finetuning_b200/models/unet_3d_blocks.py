@@ -33,9 +33,17 @@ class StepContext:
 
 
 def _maybe_ckpt(enabled, fn, *args):
+    """One activation-checkpoint unit (the reference's custom_checkpoint / cross_attn_g_c / up_down_g_c granularity).  The
+    dropout seeds of the unit derive from a base seed drawn here, outside the recomputed function, so forward, recompute
+    and backward agree on every mask; torch's own RNG-state bookkeeping is switched off (it cannot be graph-captured)."""
+    base = ops.next_dropout_seed()   # drawn the same way with checkpointing on or off: both modes see the same masks
+
+    def scoped(*a):
+        with ops.dropout_seed_scope(base):
+            return fn(*a)
     if enabled:
-        return checkpoint(fn, *args, use_reentrant=False)
-    return fn(*args)
+        return checkpoint(scoped, *args, use_reentrant=False, preserve_rng_state=False)
+    return scoped(*args)
 
 
 class _Block3D(nn.Module):
@@ -280,6 +288,6 @@ def get_up_block(up_block_type, num_layers, in_channels, out_channels, prev_outp
     return _UP[up_block_type](**kw)
 
 
-def transformer_g_c(transformer, sample, num_frames):
-    """Checkpointed call of a temporal transformer (reference helper of the same name, unet_3d_blocks.py:74-78)."""
-    return checkpoint(lambda t: transformer(t, num_frames=num_frames).sample, sample, use_reentrant=False)
+def transformer_g_c(transformer, sample, num_frames, enabled=True):
+    """(Checkpointed) call of a temporal transformer (reference helper of the same name, unet_3d_blocks.py:74-78)."""
+    return _maybe_ckpt(enabled, lambda t: transformer(t, num_frames=num_frames).sample, sample)

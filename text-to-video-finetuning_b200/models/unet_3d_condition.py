@@ -138,10 +138,7 @@ class UNet3DConditionModel(ModelMixin, ConfigMixin):
 
         h = run_conv(self.conv_in, x, cin_pad=8 - cfg.in_channels)
         if num_frames > 1:
-            if self.gradient_checkpointing:
-                h = transformer_g_c(self.transformer_in, h, num_frames)
-            else:
-                h = self.transformer_in(h, num_frames=num_frames).sample
+            h = transformer_g_c(self.transformer_in, h, num_frames, self.gradient_checkpointing)
 
         # runtime.GradientBuckets: start a block's share of the gradient all-reduce as soon as its backward is through
         mark = getattr(self, "_t2v_grad_hook", None)

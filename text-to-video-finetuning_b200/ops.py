@@ -374,22 +374,64 @@ class _DropoutScaleAdd(Function):
     @staticmethod
     def forward(ctx, x, base, p, scale, seed):
         ctx.meta = (p, scale, seed, base is not None)
-        return prims.dropout_scale_add(x, base, p, scale, seed)
+        return prims.dropout_scale_add(x, base, p, scale, seed, dropout_epoch(x.device))
 
     @staticmethod
     def backward(ctx, dy):
         p, scale, seed, has_base = ctx.meta
         dy = _cont(dy)
-        return prims.dropout_scale_add(dy, None, p, scale, seed), (dy if has_base else None), None, None, None
+        return prims.dropout_scale_add(dy, None, p, scale, seed, dropout_epoch(dy.device)), (dy if has_base else None), None, None, None
 
 
-_dropout_counter = [0]
+# Dropout masks are a pure function of (host seed, device epoch, element index).
+#   * host seed: drawn from torch's default CPU generator at the call site.  Inside an activation-checkpointed sub-module the
+#     seeds derive instead from ONE base seed drawn outside the checkpointed function and handed to it as an argument
+#     (dropout_seed_scope), so the recomputed forward draws the SAME seeds and its activations match the masks the first
+#     forward (and the backward) used - without touching torch's RNG-state save/restore (not capturable in a CUDA graph).
+#   * device epoch: an int64 counter in device memory, bumped once per training step (step.DataParallelStep) and read by the
+#     kernel when it RUNS - a replayed CUDA graph (whose host seeds are baked in at capture) gets fresh masks every step.
+_epochs = {}
+
+
+def dropout_epoch(device):
+    device = torch.device(device)
+    key = (device.type, device.index)
+    t = _epochs.get(key)
+    if t is None:
+        t = _epochs[key] = torch.zeros(1, device=device, dtype=torch.int64)
+    return t
+
+
+def bump_dropout_epoch(device):
+    prims.counter_add(dropout_epoch(device), 1)
+
+
+import contextlib
+import threading
+
+_seed_scope = threading.local()
+
+
+@contextlib.contextmanager
+def dropout_seed_scope(base):
+    """Inside the scope the n-th dropout call site gets seed splitmix(base, n) - a pure function of `base`."""
+    prev = getattr(_seed_scope, "state", None)
+    _seed_scope.state = [int(base), 0]
+    try:
+        yield
+    finally:
+        _seed_scope.state = prev
 
 
 def next_dropout_seed():
-    """Seeds follow torch's global seed so runs are reproducible; each call site/step gets a fresh stream."""
-    _dropout_counter[0] += 1
-    return (torch.initial_seed() * 1000003 + _dropout_counter[0]) & 0x7FFFFFFFFFFFFFFF
+    st = getattr(_seed_scope, "state", None)
+    if st is None:
+        return int(torch.randint(0, 1 << 62, (1,)).item())
+    st[1] += 1
+    z = (st[0] + st[1] * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return (z ^ (z >> 31)) >> 2
 
 
 def dropout_scale_add(x, base, p, scale=1.0, seed=None):

@@ -183,14 +183,17 @@ class GradientBuckets:
 
 
 class GraphedStep:
-    """Captures `fn(*static_inputs)` (forward + backward of one clip batch) into a CUDA graph and replays it.
+    """Captures `fn(*static_inputs)` (forward + backward [+ optimizer] of one clip batch) into a CUDA graph and replays it.
 
     `fn` must be free of host synchronisation and allocate only through PyTorch's caching allocator (true for every
-    Function in ops.py).  Inputs are copied into static buffers before each replay."""
+    Function in ops.py).  Inputs are copied into static buffers before each replay.  `snapshot`: tensors that `fn` mutates
+    in place (weights, gradient buffer, optimizer state); they are saved before the warm-up / capture dry runs and restored
+    afterwards, so building the graph does not advance training."""
 
-    def __init__(self, fn, example_inputs, warmup=2):
+    def __init__(self, fn, example_inputs, warmup=2, snapshot=()):
         self.fn = fn
         self.static_in = [x.clone() for x in example_inputs]
+        saved = [t.clone() for t in snapshot]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -201,6 +204,10 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.static_out = fn(*self.static_in)
+        with torch.no_grad():
+            for t, s in zip(snapshot, saved):
+                t.copy_(s)
+        torch.cuda.synchronize()
 
     def __call__(self, *inputs):
         for dst, src in zip(self.static_in, inputs):

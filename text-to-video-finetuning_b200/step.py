@@ -42,19 +42,33 @@ def finetune_loss(unet, latents, noise, timesteps, encoder_hidden_states, alphas
 
 
 class DataParallelStep:
-    """fwd + bwd of `passes` UNet passes over one clip batch per rank, then ONE gradient all-reduce.
+    """One optimisation micro-step per call: fwd + bwd of `passes` UNet passes over one clip batch per rank; on the boundary
+    of a gradient-accumulation window ONE gradient all-reduce and, when an optimizer is attached, the fused AdamW step -
+    the whole thing captured in a CUDA graph and replayed (`use_graph`).
 
     `passes=2` reproduces the reference's two-pass video step (train.py:814-834, H3: loss = loss_0 + loss_1);
-    throughput is reported per pass with passes=1."""
+    throughput is reported per pass with passes=1.
 
-    def __init__(self, unet, alphas_cumprod, passes=1, use_graph=False, adopt=True):
+    Gradient bookkeeping (reference: accelerator.accumulate / backward / optimizer.step / zero_grad, train.py:739-879):
+      * gradients accumulate in the flat fp32 buffer across the micro-steps of a window; every loss is scaled by
+        1 / accumulation (what accelerator.backward does);
+      * the all-reduce runs only on the window's last micro-step;
+      * with an attached optim.FusedAdamW the update kernel consumes and zeroes the gradients and rewrites the bf16 shadow,
+        so neither a memset nor a cast pass remains in the step.  Without one (a torch optimizer, or fwd+bwd only) the
+        buffer is zeroed at the start of each window and the shadow is re-cast from the masters every call."""
+
+    def __init__(self, unet, alphas_cumprod, passes=1, use_graph=False, adopt=True, optimizer=None, accumulation=1):
         self.unet = unet
         self.abar = alphas_cumprod
         self.passes = passes
         self.arena = ParamArena(unet) if adopt else None
         self.use_graph = use_graph
         self.sync_gradients = True   # set False to run fwd+bwd only (profiling on a single rank)
-        self._graph = None
+        self.optimizer = optimizer
+        self.accumulation = max(1, int(accumulation))
+        self._micro = 0
+        self._graphs = {}
+        self._gscale = None
         # world > 1: per-block gradient all-reduces are issued from inside the backward pass (overlap), see GradientBuckets
         self.buckets = None
         if (self.arena is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
@@ -62,32 +76,76 @@ class DataParallelStep:
             self.buckets = GradientBuckets(self.arena, unet)
             self.buckets.install()
 
-    def _fwd_bwd(self, latents, noise, timesteps, text):
-        if self.arena is not None:
-            self.arena.zero_grads()
+    def attach_optimizer(self, optimizer):
+        self.optimizer = optimizer
+        self._graphs = {}
+
+    def _fwd_bwd(self, latents, noise, timesteps, text, first, last):
+        """first / last: position of this micro-step inside its accumulation window."""
+        fused = self.optimizer is not None and hasattr(self.optimizer, "launch")
+        if self.arena is not None and not fused:
+            if first:
+                self.arena.zero_grads()
             self.arena.refresh_shadow()
+        elif fused and first and not self.optimizer.covers_all_trainable():
+            self.arena.zero_grads()   # trainable parameters outside the optimizer would otherwise accumulate forever
+        ops.bump_dropout_epoch(latents.device)
+        if self._gscale is None or self._gscale.device != latents.device:
+            self._gscale = torch.empty((), device=latents.device, dtype=torch.float32)
+            self._gscale.fill_(1.0 / self.accumulation)
         total = None
-        overlap = self.buckets is not None and self.sync_gradients
+        reduce_now = last and self.sync_gradients
+        overlap = self.buckets is not None and reduce_now
         for i in range(self.passes):
             loss = finetune_loss(self.unet, latents, noise, timesteps, text, self.abar)
             if overlap:
                 self.buckets.armed = i == self.passes - 1   # gradients are final only in the last pass
-            loss.backward()
+            loss.backward(self._gscale if self.accumulation > 1 else None)
             total = loss.detach() if total is None else total + loss.detach()
         if overlap:
             self.buckets.finish()
+        elif reduce_now and self.arena is not None:
+            allreduce_gradients(self.arena)
+        if fused and last:
+            self.optimizer.launch(zero_grad=True)
         return total
 
     def __call__(self, latents, noise, timesteps, encoder_hidden_states):
         if self.arena is not None:
             self.arena.reattach_grads()
+        first = self._micro % self.accumulation == 0
+        last = (self._micro + 1) % self.accumulation == 0
+        self._micro += 1
+        fused = self.optimizer is not None and hasattr(self.optimizer, "launch")
+        if fused and last:
+            self.optimizer.push_hyperparams()   # learning rate of this step -> device (outside the graph)
         args = (latents, noise, timesteps, encoder_hidden_states)
         if self.use_graph:
-            if self._graph is None:
-                self._graph = GraphedStep(self._fwd_bwd, args)
-            loss = self._graph(*args)
-        else:
-            loss = self._fwd_bwd(*args)
-        if self.arena is not None and self.sync_gradients and self.buckets is None:
-            allreduce_gradients(self.arena)
-        return loss
+            key = (first, last, self.passes, self.sync_gradients, getattr(self.optimizer, "generation", 0),
+                   tuple(tuple(a.shape) for a in args))
+            g = self._graphs.get(key)
+            if g is None:
+                # the capture runs the step for real (warm-up + capture replays nothing): keep the optimizer state and the
+                # weights of those dry runs out of the training trajectory
+                g = self._graphs[key] = GraphedStep(lambda *a: self._fwd_bwd(*a, first, last), args, snapshot=self._snapshot())
+            return g(*args)
+        return self._fwd_bwd(*args, first, last)
+
+    def _snapshot(self):
+        """Tensors the dry runs of a graph capture must not change for good: weights, gradients and optimizer state."""
+        keep = []
+        if self.arena is not None:
+            keep += [self.arena.master, self.arena.grad, self.arena.shadow]
+        opt = self.optimizer
+        if opt is not None and hasattr(opt, "launch"):
+            keep += [opt.exp_avg, opt.exp_avg_sq, opt.state_dev, opt.sq]
+        keep.append(ops.dropout_epoch(self.abar.device))
+        return keep
+
+    @property
+    def _graph(self):   # bench.py / tests poke at this to drop captured graphs before tearing NCCL down
+        return self._graphs
+
+    @_graph.setter
+    def _graph(self, value):
+        self._graphs = {} if value is None else value

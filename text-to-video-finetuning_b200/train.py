@@ -77,10 +77,13 @@ def create_optimizer_params(model_list, lr):
 
 
 def _lr_lambda(kind, warmup, total):
+    """diffusers.optimization.get_scheduler semantics (train.py:626-631): plain 'constant' has no warm-up."""
     def f(step):
+        if kind == "constant":
+            return 1.0
         if step < warmup:
             return float(step) / max(1, warmup)
-        if kind == "constant" or kind == "constant_with_warmup":
+        if kind == "constant_with_warmup":
             return 1.0
         prog = (step - warmup) / max(1, total - warmup)
         if kind == "linear":
@@ -191,7 +194,10 @@ def main(
     if use_8bit_adam:
         raise NotImplementedError("bitsandbytes 8-bit Adam is not available; fused AdamW is SURVEY 8(f) row 1")
     if seed is not None:
-        torch.manual_seed(seed + rank)
+        # model construction and LoRA initialisation (lora_down ~ N(0, 1/r)) must be identical on every rank: the reference
+        # gets that from accelerate/DDP broadcasting rank 0's parameters at wrap time (train.py:661).  The per-rank stream
+        # (noise, timesteps, dropout) is seeded after the model is built.
+        torch.manual_seed(seed)
     if rank == 0:
         os.makedirs(output_dir, exist_ok=True)
 
@@ -220,17 +226,26 @@ def main(
     ], learning_rate)
 
     abar = ddpm_alphas_cumprod(device=dev)
-    stepper = DataParallelStep(unet, abar, passes=2, use_graph=False)  # parameters now live in the flat arena
-    fused_adamw = bool(kwargs.get("fused_adamw", False))   # opt-in: optim.FusedAdamW on the flat arena
+    use_graph = bool(kwargs.get("use_cuda_graph", dev.type == "cuda"))   # replay the whole step as one CUDA graph (static shapes)
+    stepper = DataParallelStep(unet, abar, passes=2, use_graph=use_graph, accumulation=gradient_accumulation_steps)
+    # parameters now live in the flat arena.  Every rank must start from rank 0's weights (DDP does this at wrap time).
+    if world > 1:
+        dist.broadcast(stepper.arena.master, src=0)
+        stepper.arena.refresh_shadow()
+    if seed is not None:
+        torch.manual_seed(seed + rank)
+    fused_adamw = bool(kwargs.get("fused_adamw", True))   # optim.FusedAdamW on the flat arena; False: torch AdamW
     if fused_adamw:
         from .optim import FusedAdamW
         optimizer = FusedAdamW(stepper.arena, groups, lr=learning_rate, betas=(adam_beta1, adam_beta2), weight_decay=adam_weight_decay,
-                               eps=adam_epsilon)
+                               eps=adam_epsilon, max_grad_norm=max_grad_norm)
+        stepper.attach_optimizer(optimizer)   # the update (clip + AdamW + shadow refresh + grad zeroing) is part of the step graph
     else:
         optimizer = torch.optim.AdamW(groups, lr=learning_rate, betas=(adam_beta1, adam_beta2), weight_decay=adam_weight_decay,
                                       eps=adam_epsilon)
-    sched = torch.optim.lr_scheduler.LambdaLR(optimizer, _lr_lambda(lr_scheduler, lr_warmup_steps * gradient_accumulation_steps,
-                                                                    max_train_steps * gradient_accumulation_steps))
+    # stepped once per OPTIMIZER step, so warm-up and total are counted in optimizer steps (the reference scales both by the
+    # accumulation factor, train.py:626-631, because accelerate steps its scheduler on every micro-step)
+    sched = torch.optim.lr_scheduler.LambdaLR(optimizer, _lr_lambda(lr_scheduler, lr_warmup_steps, max_train_steps))
 
     kinds = [dataset_types] if isinstance(dataset_types, str) else list(dataset_types)
     if cached_latent_dir:
@@ -246,9 +261,13 @@ def main(
     sampler = torch.utils.data.distributed.DistributedSampler(dataset, world, rank, shuffle=shuffle) if world > 1 else None
     loader = torch.utils.data.DataLoader(dataset, batch_size=train_batch_size, shuffle=shuffle and sampler is None, sampler=sampler)
 
-    global_step, micro = 0, 0
+    global_step, micro, epoch = 0, 0, 0
     t0 = time.time()
+    step_times = []
     while global_step < max_train_steps:
+        if sampler is not None:
+            sampler.set_epoch(epoch)   # a new shuffle every epoch
+        epoch += 1
         for batch in loader:
             latents = batch["pixel_values"].to(dev, torch.float32)
             if "text_embeds" not in batch:
@@ -258,18 +277,22 @@ def main(
             timesteps = torch.randint(0, abar.shape[0], (latents.shape[0],), device=dev, dtype=torch.int64)
             if latents.shape[2] <= 1:
                 stepper.passes = 1  # single-frame data breaks out after the first pass (train.py:832)
-            loss = stepper(latents, noise, timesteps, text)
+            t_step = time.perf_counter()
+            loss = stepper(latents, noise, timesteps, text)   # fused: on a window boundary this includes clip + AdamW
             micro += 1
             if micro % gradient_accumulation_steps:
-                continue  # gradients keep accumulating in the flat buffer
-            if fused_adamw:   # clipping is folded into the update as a gradient scale
-                optimizer.step(grad_scale=optimizer.clip_scale(max_grad_norm) if max_grad_norm is not None else 1.0)
+                continue  # gradients keep accumulating in the flat buffer (loss scaled by 1 / accumulation)
+            if fused_adamw:
+                optimizer._opt_called = True   # the update ran inside the step (graph); keeps LambdaLR's order check quiet
             else:
                 if max_grad_norm is not None:
-                    torch.nn.utils.clip_grad_norm_([p for g in optimizer.param_groups for p in g["params"]], max_grad_norm)
+                    torch.nn.utils.clip_grad_norm_([p for g in optimizer.param_groups for p in g["params"] if p.grad is not None], max_grad_norm)
                 optimizer.step()
             sched.step()
             global_step += 1
+            if kwargs.get("_time_steps"):   # test hook: synchronous per-step wall time (tests/test_train_loop.py)
+                torch.cuda.synchronize()
+                step_times.append(time.perf_counter() - t_step)
             if rank == 0 and (global_step % 10 == 0 or global_step == 1):
                 print(f"step {global_step}/{max_train_steps} loss {loss.item():.5f} ({(time.time() - t0) / global_step:.3f} s/step)")
             if rank == 0 and global_step % checkpointing_steps == 0:
@@ -280,17 +303,18 @@ def main(
         dist.barrier()
     if rank == 0:
         save_checkpoint(unet, lora_manager, output_dir, global_step, use_unet_lora, save_pretrained_model, final=True)
+    return {"steps": global_step, "step_times": step_times, "stepper": stepper, "optimizer": optimizer}
 
 
 def save_checkpoint(unet, lora_manager, output_dir, step, use_unet_lora, save_pretrained_model, final=False):
     """LoRA in the cloneofsimo list format (`lora/<step>_unet.pt`), UNet in diffusers layout (`unet/`)."""
     path = output_dir if final else os.path.join(output_dir, f"checkpoint-{step}")
     os.makedirs(path, exist_ok=True)
-    if use_unet_lora:
+    if use_unet_lora:   # the reference saves the LoRA files and (save_pretrained_model) the pipeline: train.py:908-958
         from .utils.lora import save_lora_weight
         os.makedirs(os.path.join(path, "lora"), exist_ok=True)
         save_lora_weight(unet, os.path.join(path, "lora", f"{step}_unet.pt"), lora_manager.unet_replace_modules)
-    elif save_pretrained_model:
+    if save_pretrained_model:
         unet.save_pretrained(os.path.join(path, "unet"))
 
 
