@@ -507,8 +507,8 @@ def main():
             loss_rel = abs(parity_gpu[0] - loss_ref) / abs(loss_ref)
             gn_rel = abs(parity_gpu[1] - gn_ref) / gn_ref
             parity = {"loss": parity_gpu[0], "loss_oracle": loss_ref, "loss_rel": loss_rel, "grad_norm": parity_gpu[1],
-                      "grad_norm_oracle": gn_ref, "grad_norm_rel": gn_rel, "tolerance": {"loss_rel": 1e-3, "grad_norm_rel": 5e-3},
-                      "status": "green" if (loss_rel <= 1e-3 and gn_rel <= 5e-3) else "red",
+                      "grad_norm_oracle": gn_ref, "grad_norm_rel": gn_rel, "tolerance": {"loss_rel": 1e-3, "grad_norm_rel": 1e-3},
+                      "status": "green" if (loss_rel <= 1e-3 and gn_rel <= 1e-3) else "red",
                       "what": "full benchmark configuration (1.41 B parameters, 16 frames, 32x32 latents), dropout off, same weights and "
                               "inputs; bf16 kernels vs the fp32 CPU oracle"}
         else:

@@ -34,6 +34,10 @@ int t2v_version(void);
 const char* t2v_last_error(void);
 /* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
 int64_t t2v_launch_count(void);
+/* Identifier of the CUDA-graph capture `stream` is currently part of, 0 when it is not capturing.  The host layer uses it to
+ * keep zero-initialised scratch (GroupNorm statistics) from crossing a capture boundary: memory zeroed by a memset node of
+ * one graph is not zero for launches outside that graph.                                                            */
+int64_t t2v_stream_capture_id(void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Fused epilogue shared by the tensor-core entry points:  y = alpha * acc + bias[c] + rowbias[n][c] + residual
@@ -49,6 +53,15 @@ typedef struct {
     void* workspace;        /* optional scratch of t2v_conv_workspace_bytes(...) bytes: lets conv_fwd / conv_dgrad
                                split the reduction over SMs when the output has few tiles (deep, small maps)   */
     int64_t workspace_bytes;
+    /* GroupNorm input statistics of the OUTPUT, produced by the epilogue (conv_fwd only; NULL: none): for output row r (rows
+     * flattened in [N][Ho][Wo] order) and column c
+     *     stats[((r / stats_rows) * stats_ld + c) * 2 + {0, 1}] += {y, y*y}          (fp32, red.add; zero the buffer first)
+     * i.e. one (sum, sum of squares) pair per frame and channel; stats_rows = output rows per frame.  The consumer GroupNorm
+     * (t2v_groupnorm_fwd) finalises them per frame or per clip, so its statistics pass over the tensor disappears.       */
+    float* stats;
+    int64_t stats_ld;
+    int32_t stats_rows;
+    int32_t pad_;
 } T2VEpilogue;
 
 /* Implicit-GEMM convolution forward on tcgen05 tensor cores (TMA-fed, zero padding by TMA OOB fill).
@@ -123,15 +136,23 @@ int t2v_flash_attn_bwd(const void* q, const void* k, const void* v, const void* 
  * ResnetBlock2D.norm1/norm2 (per frame: S = B*F), Transformer2DModel.norm (eps 1e-6), TemporalConvLayer /
  * TransformerTemporalModel.norm (per clip: S = B, P = F*H*W) and conv_norm_out (unet_3d_condition.py:239-243,488-490).
  * stat [S][G][2] = (mean, rstd), ab [S][C][2] = per-channel affine with y = act(a x + b) (both saved for backward).
- * workspace: t2v_groupnorm_workspace_bytes(S, P, C) bytes, ZERO on entry; every call leaves it zero again, so one
- * zero-initialised buffer can be reused by all GroupNorm calls of a stream (no memset per call).                  */
+ * Two kernels per direction: per-channel sums (red.add into zeroed fp32 scratch) and a finalise + apply pass.  The forward
+ * sums are skipped when the producer of x already emitted them (T2VEpilogue.stats): stats0 / stats1 then hold the per-frame
+ * (sum, sum of squares) of channels [0, C0) and [C0, C) - two sources for a channel concatenation - with `fps` frames per
+ * normalisation sample (1: per-frame norm, F: per-clip norm) and row pitches ld0 / ld1 in channels.
+ * workspace: t2v_groupnorm_workspace_bytes(S, P, C) bytes, ZERO on entry, garbage afterwards (forward needs it only when
+ * stats0 is NULL).                                                                                                  */
 int64_t t2v_groupnorm_workspace_bytes(int32_t S, int64_t P, int32_t C);
-int t2v_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stat, float* ab, void* workspace,
-                      int32_t S, int64_t P, int32_t C, int32_t G, float eps, int32_t silu, void* stream);
+int t2v_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stat, float* ab, const float* stats0,
+                      int32_t C0, int64_t ld0, const float* stats1, int64_t ld1, int32_t fps, void* workspace, int32_t S, int64_t P,
+                      int32_t C, int32_t G, float eps, int32_t silu, void* stream);
 /* dx = d/dx [act(GN(x))]^T dy (+ add); dgamma / dbeta (fp32) are accumulated (+=) and may be NULL.               */
 int t2v_groupnorm_bwd(const void* dy, const void* x, const float* gamma, const float* stat, const float* ab, const void* add,
                       void* dx, float* dgamma, float* dbeta, void* workspace, int32_t S, int64_t P, int32_t C, int32_t G,
                       int32_t silu, void* stream);
+/* stats[(s * ld + c) * 2 + {0,1}] += sum over the P pixels of sample s of {x, x*x}: the statistics pass on its own (what
+ * T2VEpilogue.stats produces inside a GEMM epilogue), for GroupNorm inputs that do not come out of a GEMM.            */
+int t2v_channel_stats(const void* x, float* stats, int32_t S, int64_t P, int32_t C, int64_t ld, void* stream);
 
 /* LayerNorm over rows of x [rows][C] (BasicTransformerBlock.norm1/2/3, eps 1e-5); stat [rows][2] = (mean, rstd).  */
 int t2v_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stat, int64_t rows, int32_t C,

@@ -23,7 +23,21 @@ def _conv_f32(x, w, stride, pads):
     return F.conv2d(xf, w.float().permute(0, 3, 1, 2), stride=stride).permute(0, 2, 3, 1)
 
 
-def conv_fwd(x, w, bias=None, rowbias=None, residual=None, stride=1, pads=(0, 0, 0, 0), alpha=1.0, out_fp32=False, rowbias_div=1):
+def stats_alloc(frames, C, device):
+    return torch.zeros((frames, C, 2), dtype=torch.float32, device=device)
+
+
+def zeros_f32(shape, device):
+    return torch.zeros(shape, dtype=torch.float32, device=device)
+
+
+def channel_stats(x):
+    xf = x.float()
+    return torch.stack([xf.sum(dim=1), (xf * xf).sum(dim=1)], dim=-1).contiguous()
+
+
+def conv_fwd(x, w, bias=None, rowbias=None, residual=None, stride=1, pads=(0, 0, 0, 0), alpha=1.0, out_fp32=False, rowbias_div=1,
+             stats=None, stats_rows=0):
     y = alpha * _conv_f32(x, w, stride, pads)
     if bias is not None:
         y = y + bias
@@ -32,6 +46,9 @@ def conv_fwd(x, w, bias=None, rowbias=None, residual=None, stride=1, pads=(0, 0,
         y = y + rowbias[idx][:, None, None, :]
     if residual is not None:
         y = y + residual.float()
+    if stats is not None:   # epilogue statistics: per-(frame, channel) sums of the fp32 values, rows flattened in [N][Ho][Wo] order
+        yf = y.reshape(-1, stats_rows, y.shape[-1])
+        stats += torch.stack([yf.sum(dim=1), (yf * yf).sum(dim=1)], dim=-1)
     return y.contiguous() if out_fp32 else y.to(BF).contiguous()
 
 
@@ -86,9 +103,23 @@ def _gn_apply(x3, gamma, beta, G, eps, silu):
     return y, mean.view(S, G), rstd.view(S, G)
 
 
-def groupnorm_fwd(x, gamma, beta, G, eps, silu):
+def groupnorm_fwd(x, gamma, beta, G, eps, silu, stats=None, fps=1):
     S, P, C = x.shape
-    y, mean, rstd = _gn_apply(x, gamma.float(), beta.float(), G, eps, silu)
+    if stats:   # the producer's sums ARE the statistics (as in the kernel): a wiring mistake upstream shows up in y
+        st = torch.cat([t.view(S, fps, t.shape[1], 2).sum(dim=1) for t in stats], dim=1).double()      # [S, C, 2]
+        cpg = C // G
+        n = float(P * cpg)
+        gsum = st.view(S, G, cpg, 2).sum(dim=2)
+        mean = gsum[..., 0] / n
+        var = (gsum[..., 1] / n - mean * mean).clamp_min(0)
+        rstd = (1.0 / torch.sqrt(var + eps)).float()
+        mean = mean.float()
+        xh = (x.float().view(S, P, G, cpg) - mean[:, None, :, None]) * rstd[:, None, :, None]
+        y = xh.view(S, P, C) * gamma.float() + beta.float()
+        if silu:
+            y = y * torch.sigmoid(y)
+    else:
+        y, mean, rstd = _gn_apply(x, gamma.float(), beta.float(), G, eps, silu)
     stat = torch.stack([mean, rstd], dim=-1).contiguous()
     cpg = C // G
     a = rstd.repeat_interleave(cpg, dim=1) * gamma.float()

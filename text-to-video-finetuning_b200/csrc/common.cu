@@ -44,7 +44,16 @@ int64_t launches();
 }
 
 extern "C" {
-int t2v_version(void) { return 1; }
+int t2v_version(void) { return 2; }
 const char* t2v_last_error(void) { return t2v::last_error(); }
 int64_t t2v_launch_count(void) { return t2v::launches(); }
+int64_t t2v_stream_capture_id(void* stream) {
+    cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+    unsigned long long id = 0;
+    if (cudaStreamGetCaptureInfo(static_cast<cudaStream_t>(stream), &status, &id) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return status == cudaStreamCaptureStatusActive ? static_cast<int64_t>(id) : 0;
+}
 }

@@ -12,6 +12,10 @@
 
 using namespace t2v;
 
+namespace t2v {
+int launch_channel_stats(const void* x, float* stats, int S, int64_t P, int C, int64_t ld, cudaStream_t st);  // norms.cu
+}
+
 namespace {
 
 struct Box3 {
@@ -212,6 +216,78 @@ void apply_fwd_splits(GemmParams& p, int splits, int kb_total) {
     p.ksplit_var = 4;
 }
 
+// GroupNorm statistics in the epilogue (T2VEpilogue.stats): express "frame of an output row" in the tile's row coordinates
+// and check that aligned runs of 32 (or 16) accumulator rows never straddle two frames.  Returns false when this tiling
+// cannot do it (the caller then runs the standalone statistics pass over the finished output).
+bool plan_epilogue_stats(GemmParams& p, const T2VEpilogue* e, int Wo, int Ho, int N) {
+    if (!e || !e->stats || e->stats_rows <= 0) return false;
+    const int64_t pf = e->stats_rows;
+    int cw = 0, ch = 0, cn = 0, div = 1;
+    int64_t run;   // accumulator rows (in tile row order: w fastest, then h, then n) that share a frame
+    if (pf == int64_t(Wo) * Ho) {
+        cn = 1;
+        run = int64_t(p.bw) * p.bh;
+    } else if (pf == Wo) {
+        ch = 1; cn = Ho;
+        run = p.bw;
+    } else if (Ho == 1 && N == 1 && Wo % pf == 0) {
+        cw = 1; div = int(pf);
+        run = p.bh == 1 && p.bn == 1 ? pf : 0;
+    } else {
+        return false;
+    }
+    int seg = 0;
+    if (run > 0 && run % 32 == 0) seg = 32;
+    else if (run > 0 && run % 16 == 0) seg = 16;
+    if (!seg) return false;
+    p.stats = e->stats;
+    p.st_ld = e->stats_ld;
+    p.st_cw = cw; p.st_ch = ch; p.st_cn = cn; p.st_div = div; p.st_seg = seg;
+    p.flags |= EPI_STATS;
+    return true;
+}
+
+// Finishing pass of a split-K problem that also produces the GroupNorm statistics of its output: a block owns `rpb`
+// consecutive rows of ONE frame and all columns; a thread owns column quads and walks the rows.
+__global__ void splitk_finish_stats_kernel(const float* __restrict__ acc, const float* __restrict__ bias, const float* __restrict__ rowbias,
+                                           const __nv_bfloat16* __restrict__ residual, void* __restrict__ out, int64_t rows, int C,
+                                           int64_t rows_per_sample, int rb_div, int64_t rb_ld, float alpha, int out_fp32,
+                                           float* __restrict__ stats, int64_t st_ld, int st_rows, int rpb) {
+    pdl_sync();
+    const int64_t r0 = int64_t(blockIdx.x) * rpb;
+    const int64_t r1 = min(rows, r0 + rpb);
+    float* sp = stats + (r0 / st_rows) * st_ld * 2;
+    for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + c));
+        float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int64_t r = r0; r < r1; ++r) {
+            float4 v = __ldcg(reinterpret_cast<const float4*>(acc + r * C + c));
+            v.x = v.x * alpha + b4.x; v.y = v.y * alpha + b4.y; v.z = v.z * alpha + b4.z; v.w = v.w * alpha + b4.w;
+            if (rowbias) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(rowbias + (r / rows_per_sample / rb_div) * rb_ld + c));
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            }
+            if (residual) {
+                const uint2 w = __ldg(reinterpret_cast<const uint2*>(residual + r * C + c));
+                v.x += bf16_lo(w.x); v.y += bf16_hi(w.x); v.z += bf16_lo(w.y); v.w += bf16_hi(w.y);
+            }
+            if (out_fp32) {
+                reinterpret_cast<float4*>(static_cast<float*>(out) + r * C)[c >> 2] = v;
+            } else {
+                uint2 w;
+                w.x = pack_bf16(v.x, v.y);
+                w.y = pack_bf16(v.z, v.w);
+                reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out) + r * C)[c >> 2] = w;
+            }
+            s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+            q[0] += v.x * v.x; q[1] += v.y * v.y; q[2] += v.z * v.z; q[3] += v.w * v.w;
+        }
+        red_add_f32x4(sp + 2 * c, s[0], q[0], s[1], q[1]);
+        red_add_f32x4(sp + 2 * c + 4, s[2], q[2], s[3], q[3]);
+    }
+}
+
 __global__ void splitk_finish_kernel(const float* __restrict__ acc, const float* __restrict__ bias, const float* __restrict__ rowbias,
                                      const __nv_bfloat16* __restrict__ residual, void* __restrict__ out, int64_t rows, int C,
                                      int64_t rows_per_sample, int rb_div, int64_t rb_ld, float alpha, int out_fp32) {
@@ -259,6 +335,17 @@ int launch_split(GemmParams& p, bool a_mn, bool b_mn, const T2VEpilogue& e, void
     p.flags = 0;
     set_vec_flag(p);
     if (int r = launch_checked(launch_gemm(p, a_mn, b_mn, st), what)) return r;
+    if (e.stats && e.stats_rows > 0 && e.stats_ld % 2 == 0 && (reinterpret_cast<uintptr_t>(e.stats) & 15u) == 0) {
+        int rpb = 0;   // rows per block: a divisor of the frame's rows, so a block never straddles two frames
+        for (int cand : {16, 8, 4, 2, 1})
+            if (e.stats_rows % cand == 0) { rpb = cand; break; }
+        const int64_t blocks = (rows + rpb - 1) / rpb;
+        const int rc = int(launch_pdl(splitk_finish_stats_kernel, dim3(unsigned(blocks)), dim3(std::min(256, std::max(32, C / 4))), 0, st,
+                                      static_cast<const float*>(e.workspace), e.bias, e.rowbias, static_cast<const __nv_bfloat16*>(e.residual),
+                                      out, rows, C, rows_per_sample, e.rowbias_div > 0 ? e.rowbias_div : 1, int64_t(C), e.alpha, e.out_fp32,
+                                      e.stats, e.stats_ld, e.stats_rows, rpb));
+        return launch_checked(rc, what);
+    }
     const int64_t vec = rows * (C / 4);
     const int grid = int(std::min<int64_t>((vec + 255) / 256, 148 * 8));
     const int rc = int(launch_pdl(splitk_finish_kernel, dim3(grid), dim3(256), 0, st, static_cast<const float*>(e.workspace), e.bias,
@@ -338,7 +425,19 @@ static int conv_fwd_impl(const void* x, const void* w, void* y, int32_t N, int32
         return launch_split(p, false, false, *epi, y, int64_t(N) * Ho * Wo, Cout, int64_t(Ho) * Wo, static_cast<cudaStream_t>(stream), "conv_fwd");
     }
     set_vec_flag(p);
-    return launch_checked(launch_gemm(p, false, false, static_cast<cudaStream_t>(stream)), "conv_fwd");
+    bool stats_fallback = false;
+    if (epi && epi->stats) {
+        if (!(p.flags & EPI_VEC) || epi->out_fp32 || !plan_epilogue_stats(p, epi, Wo, Ho, N)) stats_fallback = true;
+    }
+    if (int r = launch_checked(launch_gemm(p, false, false, static_cast<cudaStream_t>(stream)), "conv_fwd")) return r;
+    if (stats_fallback) {   // this tiling cannot produce the statistics in the epilogue: one extra read of the (L2-hot) output
+        if (epi->out_fp32 || epi->stats_rows <= 0 || (int64_t(N) * Ho * Wo) % epi->stats_rows)
+            return fail(-2, "conv_fwd: statistics requested for an unsupported output (fp32 or ragged frames)");
+        const int frames = int(int64_t(N) * Ho * Wo / epi->stats_rows);
+        return launch_checked(launch_channel_stats(y, epi->stats, frames, epi->stats_rows, Cout, epi->stats_ld, static_cast<cudaStream_t>(stream)),
+                              "conv_fwd(stats)");
+    }
+    return 0;
 }
 
 static int conv_dgrad_impl(const void* dy, const void* w, void* dx, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,

@@ -68,6 +68,21 @@ __device__ __forceinline__ void issue_boxes(const TmaOperand& op, const int32_t*
     }
 }
 
+// One step of the transposing warp reduction used for the GroupNorm statistics: 2*CNT per-lane partial column sums become
+// CNT, lanes XOR apart exchange the half they do not keep.  After the steps (16,16)(8,8)(4,4)(2,2)(1,1) lane L holds in s[0]
+// the sum over all 32 lanes (rows) of column L; after (16,8)(8,4)(4,2)(2,1) it holds in s[0], s[1] the sums over its own
+// 16-lane half of columns 2*(L%16) and 2*(L%16)+1.
+template <int CNT, int XOR>
+__device__ __forceinline__ void xreduce_step(float (&s)[32], uint32_t lane) {
+    const bool up = (lane & XOR) != 0;
+#pragma unroll
+    for (int j = 0; j < CNT; ++j) {
+        const float send = up ? s[j] : s[j + CNT];
+        const float keep = up ? s[j + CNT] : s[j];
+        s[j] = keep + __shfl_xor_sync(0xffffffffu, send, XOR);
+    }
+}
+
 // Epilogue of one CTA (warps 2..9).  mh == 1: the two groups of four warps split the accumulator columns; mh == 2: group g
 // drains row half g.  Within a group warp w owns TMEM lanes 32*(w%4)..+31, i.e. thread <-> output row.  Output rows are
 // strided in global memory, so every 32-column chunk goes through a per-warp swizzled staging tile and is moved with
@@ -88,6 +103,7 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
     const int32_t rn = static_cast<int32_t>(row) / (p.bw * p.bh);
     const bool has_bias = p.flags & EPI_BIAS, has_rb = p.flags & EPI_ROWBIAS, has_res = p.flags & EPI_RESIDUAL;
     const bool vec = p.flags & EPI_VEC;
+    const bool has_stats = (p.flags & EPI_STATS) && vec;
     const int nchunks = (p.block_n + 31) >> 5;
     const int c_begin = (p.mh == 2 || grp == 0) ? 0 : (nchunks + 1) >> 1;
     const int c_end = p.mh == 2 ? nchunks : (grp == 0 ? (nchunks + 1) >> 1 : nchunks);
@@ -119,6 +135,13 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
             ok_s |= (__shfl_sync(0xffffffffu, row_ok ? 1u : 0u, r) & 1u) << i;
         }
         const int32_t col0 = tv.t[0] * p.block_n;
+        // GroupNorm statistics: frame of this lane's segment (taken from the segment's first row, which is in bounds
+        // whenever any row of the segment is)
+        int64_t st_off = 0;
+        if (has_stats) {
+            const int32_t fr = (gw * p.st_cw + gh * p.st_ch + gn * p.st_cn) / p.st_div;
+            st_off = int64_t(__shfl_sync(0xffffffffu, fr, lane & ~uint32_t(p.st_seg - 1))) * p.st_ld;
+        }
         const uint32_t as = p.nacc == 2 ? (it & 1u) : 0u;
         const uint32_t aphase = p.nacc == 2 ? ((it >> 1) & 1u) : (it & 1u);
         mbar_wait(&acc_full[as], aphase);
@@ -180,6 +203,31 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
                         v[8 * j + 6] += bf16_lo(q.w); v[8 * j + 7] += bf16_hi(q.w);
                     }
                     __syncwarp();
+                }
+                if (has_stats) {   // per-(frame, channel) sum and sum of squares of the final fp32 values of this chunk
+                    float s1[32], s2[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float t = row_ok ? v[j] : 0.f;
+                        s1[j] = t;
+                        s2[j] = t * t;
+                    }
+                    float* sp = p.stats + (st_off + col) * 2;
+                    if (p.st_seg == 32) {
+                        xreduce_step<16, 16>(s1, lane); xreduce_step<16, 16>(s2, lane);
+                        xreduce_step<8, 8>(s1, lane);   xreduce_step<8, 8>(s2, lane);
+                        xreduce_step<4, 4>(s1, lane);   xreduce_step<4, 4>(s2, lane);
+                        xreduce_step<2, 2>(s1, lane);   xreduce_step<2, 2>(s2, lane);
+                        xreduce_step<1, 1>(s1, lane);   xreduce_step<1, 1>(s2, lane);
+                        if (static_cast<int32_t>(lane) < cvalid) red_add_f32x2(sp + 2 * lane, s1[0], s2[0]);
+                    } else {
+                        xreduce_step<16, 8>(s1, lane);  xreduce_step<16, 8>(s2, lane);
+                        xreduce_step<8, 4>(s1, lane);   xreduce_step<8, 4>(s2, lane);
+                        xreduce_step<4, 2>(s1, lane);   xreduce_step<4, 2>(s2, lane);
+                        xreduce_step<2, 1>(s1, lane);   xreduce_step<2, 1>(s2, lane);
+                        const int c = 2 * (lane & 15);
+                        if (c < cvalid) red_add_f32x4(sp + 2 * c, s1[0], s2[0], s1[1], s2[1]);
+                    }
                 }
                 // own row -> staging
                 if (ESZ == 2) {
@@ -464,15 +512,13 @@ int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
 
 template <bool A_MN, bool B_MN>
 static int launch_impl(const GemmParams& p, cudaStream_t stream) {
-    static bool attr_set = false;
+    static std::once_flag attr_once;   // forward runs on the Python thread, backward on autograd worker threads
+    static cudaError_t attr_err = cudaSuccess;
     const size_t smem = static_cast<size_t>(p.num_stages) * (p.stage_bytes_a + p.stage_bytes_b) + 1024 /*align*/ + 256 /*barriers*/ +
                         kEpilogueStagingBytes;
     auto kern = gemm_tc_kernel<A_MN, B_MN>;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-        if (e != cudaSuccess) return static_cast<int>(e);
-        attr_set = true;
-    }
+    std::call_once(attr_once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); });
+    if (attr_err != cudaSuccess) return static_cast<int>(attr_err);
     int grid = p.num_tiles < device_sm_count() ? p.num_tiles : device_sm_count();
     if (grid < 1) return 0;
     return static_cast<int>(launch_pdl(kern, dim3(grid), dim3(kNumThreads), smem, stream, p));

@@ -46,6 +46,7 @@ enum EpiFlags : int32_t {
     EPI_ROWBIAS = 2,    // + rowbias[gn * rb_ld + col]        (fp32; e.g. per-frame time-embedding projection)
     EPI_RESIDUAL = 4,   // + residual[same offset as out]     (bf16)
     EPI_VEC = 8,        // 16-byte vector access is legal for out/residual
+    EPI_STATS = 16,     // accumulate per-(frame, channel) sum / sum of squares of the output into `stats` (GroupNorm input statistics)
 };
 
 struct alignas(64) GemmParams {
@@ -85,6 +86,13 @@ struct alignas(64) GemmParams {
     const void* residual;
     const float* bias;
     const float* rowbias;
+    // EPI_STATS: stats[(frame * st_ld + column) * 2 + {0, 1}] += {sum, sum of squares} over the rows of the tile, where
+    // frame = (gw * st_cw + gh * st_ch + gn * st_cn) / st_div.  The planner guarantees that every aligned run of st_seg
+    // (32 or 16) consecutive accumulator rows of a tile belongs to one frame.
+    float* stats;
+    int64_t st_ld;
+    int32_t st_cw, st_ch, st_cn, st_div, st_seg;
+    int32_t pad3_;
 };
 
 // Launches the kernel (grid = min(num_tiles, #SMs) persistent CTAs).  Returns cudaError_t as int.

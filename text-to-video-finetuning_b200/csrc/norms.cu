@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cuda_bf16.h>
+#include <mutex>
 
 namespace t2v {
 
@@ -26,13 +27,13 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 __device__ __forceinline__ float sigmoidf_(float z) { return 1.0f / (1.0f + __expf(-z)); }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm
-// ONE kernel per direction: every block is resident at once (grid <= SMs x occupancy),
-// so the blocks of a sample can meet at a spin barrier between the two passes over their own pixels:
-//   pass 1  per-channel sums over the block's chunk of pixels, reduced in shared memory, one red.global.add per channel
-//           and block into accum[S][C][2]           fwd: (sum x, sum x^2)      bwd: (sum dz, sum dz*xhat)
-//   barrier per-sample arrival counter (workspace), bounded spin
-//   pass 2  every block finalises its sample's group statistics / coefficients from accum (fp64 group combine) and
-//           streams its chunk again - the second read hits L2 (the first pass just pulled it in)
+// Two kernels per direction, chained with programmatic dependent launch:
+//   sums     per-channel sums over a block's chunk of pixels, reduced in shared memory, one red.global.add.v2 per channel
+//            and block into accum[S][C][2]          fwd: (sum x, sum x^2)      bwd: (sum dz, sum dz*xhat)
+//            The forward sums are usually NOT run: the GEMM that produced x has already accumulated them per frame and
+//            channel in its epilogue (gemm_tc.cu, EPI_STATS), so GroupNorm forward is one read + one write of the tensor.
+//   apply    every block finalises its sample's group statistics / coefficients from the sums (fp64 group combine, one
+//            L2 round trip) and streams its chunk of pixels once.
 // Thread layout: V = C/8 channel vectors; thread owns vector tid % V (coefficients live in registers) and pixel lane
 // tid / V; loads are 16 bytes, 4 pixels in flight per thread.
 constexpr int kGnThreads = 512;
@@ -46,44 +47,22 @@ struct GnArgs {
     const float* beta;
     float* stat;              // [S][G][2] (mean, rstd): written by fwd, read by bwd
     float* ab;                // [S][C][2] (a, b) with z = a x + b: written by fwd, read by bwd
-    float* accum;             // [S][C][2] workspace (zero on entry, zero again on exit)
-    unsigned* arrive;         // [S] workspace: blocks of the sample that finished pass 1
-    unsigned* done;           // [S] workspace: blocks of the sample that finished reading accum
+    float* accum;             // sums kernel output / bwd apply input: [S][C][2]
+    const float* stats0;      // fwd apply input: per-frame sums of channels [0, C0), row pitch ld0 channels
+    const float* stats1;      // ... of channels [C0, C), row pitch ld1 (NULL when C0 == C)
+    int64_t ld0, ld1;
     float* dgamma;
     float* dbeta;
     int64_t P;
-    int C, G, chunk_pixels, chunks, silu;
+    int C, C0, G, fps, chunk_pixels, chunks, silu;
     float eps;
 };
 
-__device__ __forceinline__ uint64_t globaltimer_ns() {
-    uint64_t t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
-__device__ __forceinline__ void gn_sample_barrier(unsigned* counter, unsigned target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
-        const uint64_t t0 = globaltimer_ns();
-        while (true) {
-            unsigned v;
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-            if (v >= target) break;
-            __nanosleep(64);
-            if (globaltimer_ns() - t0 > 3000000000ull) __trap();  // a resident-grid assumption was violated
-        }
-        __threadfence();
-    }
-    __syncthreads();
-}
-
+// ---- sums: MODE 0 forward (x), MODE 1 backward (dy, x, saved coefficients)
 template <int MODE>
-__global__ void __launch_bounds__(kGnThreads, 1) gn_fused_kernel(const GnArgs g) {
+__global__ void __launch_bounds__(kGnThreads, 1) gn_sums_kernel(const GnArgs g) {
     pdl_sync();
-    extern __shared__ float sh[];  // [2][C] partial sums, then [2][G] group terms
+    extern __shared__ float sh[];  // [2][C] partial sums
     const int C = g.C, G = g.G, cpg = C / G;
     const int s = blockIdx.x / g.chunks, chunk = blockIdx.x % g.chunks;
     const int V = C >> 3;
@@ -96,21 +75,18 @@ __global__ void __launch_bounds__(kGnThreads, 1) gn_fused_kernel(const GnArgs g)
     const uint4* ds = MODE == 1 ? reinterpret_cast<const uint4*>(g.dy + int64_t(s) * g.P * C) + cv : nullptr;
     for (int i = threadIdx.x; i < 2 * C; i += kGnThreads) sh[i] = 0.f;
     __syncthreads();
-
-    float a[8], b[8];  // z = a x + b (bwd: read back from the forward pass; fwd: computed after the barrier)
-    float mean[8], rstd[8];
-    if (MODE == 1 && active) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = cv * 8 + j;
-            a[j] = g.ab[(int64_t(s) * C + c) * 2];
-            b[j] = g.ab[(int64_t(s) * C + c) * 2 + 1];
-            mean[j] = g.stat[(int64_t(s) * G + c / cpg) * 2];
-            rstd[j] = g.stat[(int64_t(s) * G + c / cpg) * 2 + 1];
-        }
-    }
-    // ---- pass 1
     if (active) {
+        float a[8], b[8], mean[8], rstd[8];
+        if (MODE == 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = cv * 8 + j;
+                a[j] = g.ab[(int64_t(s) * C + c) * 2];
+                b[j] = g.ab[(int64_t(s) * C + c) * 2 + 1];
+                mean[j] = g.stat[(int64_t(s) * G + c / cpg) * 2];
+                rstd[j] = g.stat[(int64_t(s) * G + c / cpg) * 2 + 1];
+            }
+        }
         float acc0[8], acc1[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc0[j] = acc1[j] = 0.f;
@@ -155,39 +131,81 @@ __global__ void __launch_bounds__(kGnThreads, 1) gn_fused_kernel(const GnArgs g)
             if (MODE == 1) qd = __ldg(ds + p * V);
             accumulate(__ldg(xs + p * V), qd);
         }
+        if (lanes == 1) {   // one pixel lane per channel vector: no contention, plain stores
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            atomicAdd(&sh[cv * 8 + j], acc0[j]);
-            atomicAdd(&sh[C + cv * 8 + j], acc1[j]);
+            for (int j = 0; j < 8; ++j) {
+                sh[cv * 8 + j] = acc0[j];
+                sh[C + cv * 8 + j] = acc1[j];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                atomicAdd(&sh[cv * 8 + j], acc0[j]);
+                atomicAdd(&sh[C + cv * 8 + j], acc1[j]);
+            }
         }
     }
     __syncthreads();
     float* acc = g.accum + int64_t(s) * C * 2;
-    for (int c = threadIdx.x; c < C; c += kGnThreads) {
-        atomicAdd(acc + 2 * c, sh[c]);
-        atomicAdd(acc + 2 * c + 1, sh[C + c]);
-    }
-    gn_sample_barrier(g.arrive + s, unsigned(g.chunks));
+    for (int c = threadIdx.x; c < C; c += kGnThreads) red_add_f32x2(acc + 2 * c, sh[c], sh[C + c]);
+}
 
-    // ---- finalise (every block, redundantly): one L2 read per channel, fp64 group combine
-    float* t0 = sh;        // fwd: group mean   bwd: sum_c gamma * sum dz
-    float* t1 = sh + G;    // fwd: group rstd   bwd: sum_c gamma * sum dz*xhat
-    // one warp per group: lanes stride over the group's channels (one L2 read each), fp64 combine through shuffles
-    __shared__ int is_last;
-    {
+// ---- apply: MODE 0 forward, MODE 1 backward
+template <int MODE>
+__global__ void __launch_bounds__(kGnThreads, 1) gn_apply_kernel(const GnArgs g) {
+    pdl_sync();
+    extern __shared__ float sh[];
+    const int C = g.C, G = g.G, cpg = C / G;
+    const int s = blockIdx.x / g.chunks, chunk = blockIdx.x % g.chunks;
+    const int V = C >> 3;
+    const int lanes = kGnThreads / V;
+    const int cv = threadIdx.x % V, pl = threadIdx.x / V;
+    const bool active = pl < lanes;
+    const int64_t p0 = int64_t(chunk) * g.chunk_pixels;
+    const int64_t p1 = min(g.P, p0 + g.chunk_pixels);
+    const uint4* xs = reinterpret_cast<const uint4*>(g.x + int64_t(s) * g.P * C) + cv;
+    const uint4* ds = MODE == 1 ? reinterpret_cast<const uint4*>(g.dy + int64_t(s) * g.P * C) + cv : nullptr;
+    // ---- per-channel sums of this sample -> shared memory (fwd: summed over the sample's frames)
+    float* cs = sh;              // [2][C]
+    float* t0 = sh + 2 * C;      // [G]  fwd: group mean   bwd: sum_c gamma * sum dz
+    float* t1 = t0 + G;          // [G]  fwd: group rstd   bwd: sum_c gamma * sum dz*xhat
+    if (MODE == 0) {
+        for (int c = threadIdx.x; c < C; c += kGnThreads) {
+            const bool first = c < g.C0;
+            const float2* src = reinterpret_cast<const float2*>(first ? g.stats0 : g.stats1);
+            const int64_t ld = first ? g.ld0 : g.ld1;
+            const int cc = first ? c : c - g.C0;
+            float a0 = 0.f, a1 = 0.f;
+            for (int f = 0; f < g.fps; ++f) {
+                const float2 v = __ldcg(src + (int64_t(s) * g.fps + f) * ld + cc);
+                a0 += v.x;
+                a1 += v.y;
+            }
+            cs[c] = a0;
+            cs[C + c] = a1;
+        }
+    } else {
+        const float2* acc = reinterpret_cast<const float2*>(g.accum + int64_t(s) * C * 2);
+        for (int c = threadIdx.x; c < C; c += kGnThreads) {
+            const float2 v = __ldcg(acc + c);
+            cs[c] = v.x;
+            cs[C + c] = v.y;
+            if (chunk == 0) {
+                if (g.dbeta) atomicAdd(g.dbeta + c, v.x);
+                if (g.dgamma) atomicAdd(g.dgamma + c, v.y);
+            }
+        }
+    }
+    __syncthreads();
+    {   // one warp per group: fp64 combine of the group's channels through shuffles
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         for (int gi = warp; gi < G; gi += kGnThreads / 32) {
             double a0 = 0, a1 = 0;
             for (int j = lane; j < cpg; j += 32) {
                 const int c = gi * cpg + j;
-                const float2 v = __ldcg(reinterpret_cast<const float2*>(acc) + c);
                 const double w = MODE == 0 ? 1.0 : double(g.gamma[c]);
-                a0 += w * v.x;
-                a1 += w * v.y;
-                if (MODE == 1 && chunk == 0) {
-                    if (g.dbeta) atomicAdd(g.dbeta + c, v.x);
-                    if (g.dgamma) atomicAdd(g.dgamma + c, v.y);
-                }
+                a0 += w * cs[c];
+                a1 += w * cs[C + c];
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -215,20 +233,6 @@ __global__ void __launch_bounds__(kGnThreads, 1) gn_fused_kernel(const GnArgs g)
         }
     }
     __syncthreads();
-    // every read of accum by this block is done: the last block of the sample to get here puts the workspace back to zero
-    // (the contract of the workspace: zero on entry, zero on exit - no memset node per call)
-    if (threadIdx.x == 0) {
-        __threadfence();
-        is_last = atomicAdd(g.done + s, 1u) == unsigned(g.chunks) - 1u;
-    }
-    __syncthreads();
-    if (is_last) {
-        for (int i = threadIdx.x; i < 2 * C; i += kGnThreads) acc[i] = 0.f;
-        if (threadIdx.x == 0) {
-            g.arrive[s] = 0u;
-            g.done[s] = 0u;
-        }
-    }
     if (MODE == 0 && chunk == 0) {
         for (int c = threadIdx.x; c < C; c += kGnThreads) {
             const float aa = t1[c / cpg] * g.gamma[c];
@@ -237,8 +241,8 @@ __global__ void __launch_bounds__(kGnThreads, 1) gn_fused_kernel(const GnArgs g)
         }
     }
     if (!active) return;
-    // ---- pass 2
     uint4* os = reinterpret_cast<uint4*>(g.out + int64_t(s) * g.P * C) + cv;
+    float a[8], b[8];
     if (MODE == 0) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -273,10 +277,14 @@ __global__ void __launch_bounds__(kGnThreads, 1) gn_fused_kernel(const GnArgs g)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = cv * 8 + j;
-            const float q = -rstd[j] * rstd[j] * t1[c / cpg] * invn;
-            pc[j] = rstd[j] * g.gamma[c];
+            a[j] = g.ab[(int64_t(s) * C + c) * 2];
+            b[j] = g.ab[(int64_t(s) * C + c) * 2 + 1];
+            const float mean = g.stat[(int64_t(s) * G + c / cpg) * 2];
+            const float rstd = g.stat[(int64_t(s) * G + c / cpg) * 2 + 1];
+            const float q = -rstd * rstd * t1[c / cpg] * invn;
+            pc[j] = rstd * g.gamma[c];
             qc[j] = q;
-            rc[j] = -rstd[j] * t0[c / cpg] * invn - q * mean[j];
+            rc[j] = -rstd * t0[c / cpg] * invn - q * mean;
         }
         const uint4* as = g.add ? reinterpret_cast<const uint4*>(g.add + int64_t(s) * g.P * C) + cv : nullptr;
         auto apply = [&](const uint4& qx, const uint4& qd, const uint4& qa) {
@@ -456,52 +464,46 @@ __global__ void ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bf
     }
 }
 
-// Blocks that can be resident at once (the spin barrier needs the whole grid on the chip).
-// Why the barrier cannot deadlock although other kernels may share the SMs: the grid never exceeds what fits on the chip by
-// itself; kernels launched BEFORE this one on any stream terminate without waiting for it, so their SM resources free up and
-// the remaining blocks become resident; kernels launched AFTER it on the same stream (programmatic dependent launch) can
-// only start once every block of this grid has executed griddepcontrol.launch_dependents, i.e. is already resident; and a
-// concurrent kernel on the side stream (weight gradients) never waits on this one either.  The spin is bounded (3 s, then
-// trap) so that a violated assumption fails loudly instead of hanging the GPU.
-static int gn_resident_blocks() {
-    static int cached = 0;
-    if (cached) return cached;
-    cudaFuncSetAttribute(gn_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(gn_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    int per_sm0 = 0, per_sm1 = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm0, gn_fused_kernel<0>, kGnThreads, 64 * 1024);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, gn_fused_kernel<1>, kGnThreads, 64 * 1024);
-    cached = std::max(1, std::min(per_sm0, per_sm1)) * device_sm_count();
-    return cached;
+static size_t gn_smem(int C, int G) { return size_t(2 * C + 2 * G) * sizeof(float); }
+
+static void gn_set_attrs() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        cudaFuncSetAttribute(gn_sums_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(gn_sums_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(gn_apply_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(gn_apply_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    });
 }
 
-static int gn_plan(int S, int64_t P, int C, int& chunk_pixels, int& chunks) {
-    const int resident = gn_resident_blocks();
-    if (S > resident) return -1;
+// Pixel chunks per sample: about two blocks per SM overall, at least one pixel per lane (and >= 2 pixels) per block.
+static void gn_plan(int S, int64_t P, int C, int& chunk_pixels, int& chunks) {
     const int lanes = kGnThreads / (C / 8);
-    // one block per SM overall, each with at least one pixel per lane (and >= 2 pixels) so tiny maps still spread out
-    const int64_t want = std::max<int64_t>(1, resident / S);
+    const int64_t want = std::max<int64_t>(1, (2 * device_sm_count() + S - 1) / S);
     const int64_t min_px = std::max<int64_t>(2, lanes);
     const int64_t cp = std::max<int64_t>(min_px, (P + want - 1) / want);
     chunk_pixels = int(std::min<int64_t>(cp, P));
     chunks = int((P + chunk_pixels - 1) / chunk_pixels);
+}
+
+static int gn_check(const GnArgs& g) {
+    if (g.C % 8 || g.C % g.G || g.C / 8 > kGnThreads || gn_smem(g.C, g.G) > 64 * 1024)
+        return fail(-2, "groupnorm: C=%d G=%d unsupported", g.C, g.G);
     return 0;
 }
 
-static size_t gn_accum_bytes(int S, int C) { return (size_t(S) * C * 2 * sizeof(float) + 255) / 256 * 256; }
-
-template <int MODE>
-static int gn_launch(GnArgs& g, void* workspace, int S, cudaStream_t st) {
-    if (g.C % 8 || g.C % g.G || g.C / 8 > kGnThreads || 2 * g.C * sizeof(float) > 64 * 1024)
-        return fail(-2, "groupnorm: C=%d G=%d unsupported", g.C, g.G);
-    if (gn_plan(S, g.P, g.C, g.chunk_pixels, g.chunks)) return fail(-2, "groupnorm: %d samples exceed the resident grid", S);
-    const size_t ab = gn_accum_bytes(S, g.C);
-    g.accum = static_cast<float*>(workspace);
-    g.arrive = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + ab);
-    g.done = g.arrive + S;
-    launch_pdl(gn_fused_kernel<MODE>, dim3(S * g.chunks), dim3(kGnThreads), std::max<size_t>(2 * g.C, 2 * g.G) * sizeof(float), st, g);
-    count_launch(1);
-    return 0;
+// Standalone per-sample channel sums of x [S][P][C] into stats (+=), row pitch ld channels.  Used by t2v_channel_stats and
+// by conv_fwd when a problem's tiling cannot produce the statistics in the GEMM epilogue.
+int launch_channel_stats(const void* x, float* stats, int S, int64_t P, int C, int64_t ld, cudaStream_t st) {
+    if (ld != C) return fail(-2, "channel_stats: row pitch %lld != C=%d is not supported by the standalone pass", (long long)ld, C);
+    GnArgs g{};
+    g.x = static_cast<const __nv_bfloat16*>(x);
+    g.accum = stats;
+    g.P = P; g.C = C; g.G = 1;
+    if (C % 8 || C / 8 > kGnThreads || gn_smem(C, 1) > 64 * 1024) return fail(-2, "channel_stats: C=%d unsupported", C);
+    gn_set_attrs();
+    gn_plan(S, P, C, g.chunk_pixels, g.chunks);
+    return int(launch_pdl(gn_sums_kernel<0>, dim3(S * g.chunks), dim3(kGnThreads), gn_smem(C, 1), st, g));
 }
 
 }  // namespace t2v
@@ -512,23 +514,43 @@ extern "C" {
 
 int64_t t2v_groupnorm_workspace_bytes(int32_t S, int64_t P, int32_t C) {
     (void)P;
-    return int64_t(gn_accum_bytes(S, C)) + 2 * int64_t(S) * sizeof(unsigned) + 256;
+    return int64_t(S) * C * 2 * sizeof(float);
 }
 
-int t2v_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stat, float* ab, void* workspace,
-                      int32_t S, int64_t P, int32_t C, int32_t G, float eps, int32_t silu, void* stream_) {
+int t2v_channel_stats(const void* x, float* stats, int32_t S, int64_t P, int32_t C, int64_t ld, void* stream_) {
+    return launch_checked(launch_channel_stats(x, stats, S, P, C, ld, static_cast<cudaStream_t>(stream_)), "channel_stats");
+}
+
+int t2v_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stat, float* ab, const float* stats0,
+                      int32_t C0, int64_t ld0, const float* stats1, int64_t ld1, int32_t fps, void* workspace, int32_t S, int64_t P,
+                      int32_t C, int32_t G, float eps, int32_t silu, void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
     GnArgs g{};
     g.x = static_cast<const __nv_bfloat16*>(x);
     g.out = static_cast<__nv_bfloat16*>(y);
     g.gamma = gamma; g.beta = beta; g.stat = stat; g.ab = ab;
     g.P = P; g.C = C; g.G = G; g.silu = silu; g.eps = eps;
-    if (int r = gn_launch<0>(g, workspace, S, static_cast<cudaStream_t>(stream_))) return r;
-    return launch_checked(int(cudaGetLastError()), "groupnorm_fwd");
+    if (int r = gn_check(g)) return r;
+    gn_set_attrs();
+    gn_plan(S, P, C, g.chunk_pixels, g.chunks);
+    if (stats0) {
+        if (fps < 1 || C0 <= 0 || C0 > C || (C0 < C && !stats1)) return fail(-2, "groupnorm_fwd: bad statistics arguments");
+        g.stats0 = stats0; g.stats1 = stats1; g.C0 = C0; g.ld0 = ld0; g.ld1 = ld1; g.fps = fps;
+    } else {
+        if (!workspace) return fail(-3, "groupnorm_fwd: needs producer statistics or a zeroed workspace");
+        g.accum = static_cast<float*>(workspace);
+        if (int rc = int(launch_pdl(gn_sums_kernel<0>, dim3(S * g.chunks), dim3(kGnThreads), gn_smem(C, G), st, g)))
+            return launch_checked(rc, "groupnorm_fwd(sums)");
+        count_launch(1);
+        g.stats0 = g.accum; g.stats1 = nullptr; g.C0 = C; g.ld0 = C; g.ld1 = 0; g.fps = 1;
+    }
+    return launch_checked(int(launch_pdl(gn_apply_kernel<0>, dim3(S * g.chunks), dim3(kGnThreads), gn_smem(C, G), st, g)), "groupnorm_fwd");
 }
 
 int t2v_groupnorm_bwd(const void* dy, const void* x, const float* gamma, const float* stat, const float* ab, const void* add,
                       void* dx, float* dgamma, float* dbeta, void* workspace, int32_t S, int64_t P, int32_t C, int32_t G,
                       int32_t silu, void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
     GnArgs g{};
     g.x = static_cast<const __nv_bfloat16*>(x);
     g.dy = static_cast<const __nv_bfloat16*>(dy);
@@ -537,8 +559,15 @@ int t2v_groupnorm_bwd(const void* dy, const void* x, const float* gamma, const f
     g.gamma = gamma; g.stat = const_cast<float*>(stat); g.ab = const_cast<float*>(ab);
     g.dgamma = dgamma; g.dbeta = dbeta;
     g.P = P; g.C = C; g.G = G; g.silu = silu;
-    if (int r = gn_launch<1>(g, workspace, S, static_cast<cudaStream_t>(stream_))) return r;
-    return launch_checked(int(cudaGetLastError()), "groupnorm_bwd");
+    if (int r = gn_check(g)) return r;
+    if (!workspace) return fail(-3, "groupnorm_bwd: needs a zeroed workspace");
+    gn_set_attrs();
+    gn_plan(S, P, C, g.chunk_pixels, g.chunks);
+    g.accum = static_cast<float*>(workspace);
+    if (int rc = int(launch_pdl(gn_sums_kernel<1>, dim3(S * g.chunks), dim3(kGnThreads), gn_smem(C, G), st, g)))
+        return launch_checked(rc, "groupnorm_bwd(sums)");
+    count_launch(1);
+    return launch_checked(int(launch_pdl(gn_apply_kernel<1>, dim3(S * g.chunks), dim3(kGnThreads), gn_smem(C, G), st, g)), "groupnorm_bwd");
 }
 
 #define LN_DISPATCH(KERNEL, GRID, SMEM, ST, ...)                                                       \

@@ -39,20 +39,21 @@ def _lora_base(m):
     return m.linear if hasattr(m, "linear") else m.conv
 
 
-def run_linear(m, x, residual=None, out_fp32=False):
-    """Apply an nn.Linear (or a cloneofsimo-style LoRA wrapper around one) to a token matrix."""
+def run_linear(m, x, residual=None, out_fp32=False, stats_rows=0):
+    """Apply an nn.Linear (or a cloneofsimo-style LoRA wrapper around one) to a token matrix.  stats_rows > 0: the output
+    feeds a GroupNorm - let the GEMM epilogue produce its per-frame channel sums (stats_rows = tokens per frame)."""
     if _is_lora(m):
         from .utils.lora import lora_linear_forward
-        return lora_linear_forward(m, x, residual, out_fp32)
-    return ops.linear(x, m.weight, m.bias, residual, out_fp32)
+        return lora_linear_forward(m, x, residual, out_fp32, stats_rows)
+    return ops.linear(x, m.weight, m.bias, residual, out_fp32, stats_rows=stats_rows)
 
 
-def run_conv(m, x, rowbias=None, residual=None, stride=1, pads=(1, 1, 1, 1), rb_div=1, cin_pad=0, cout_pad=0):
-    """Apply an nn.Conv2d / nn.Conv3d((3,1,1)) (or its LoRA wrapper) to a channels-last batch."""
+def run_conv(m, x, rowbias=None, residual=None, stride=1, pads=(1, 1, 1, 1), rb_div=1, cin_pad=0, cout_pad=0, stats_rows=0):
+    """Apply an nn.Conv2d / nn.Conv3d((3,1,1)) (or its LoRA wrapper) to a channels-last batch (stats_rows: see run_linear)."""
     if _is_lora(m):
         from .utils.lora import lora_conv_forward
-        return lora_conv_forward(m, x, rowbias, residual, stride, pads, rb_div, cin_pad, cout_pad)
-    return ops.conv(x, m.weight, m.bias, rowbias, residual, stride, pads, rb_div, False, cin_pad, cout_pad)
+        return lora_conv_forward(m, x, rowbias, residual, stride, pads, rb_div, cin_pad, cout_pad, stats_rows)
+    return ops.conv(x, m.weight, m.bias, rowbias, residual, stride, pads, rb_div, False, cin_pad, cout_pad, stats_rows=stats_rows)
 
 
 def run_group_norm(m, x, silu, samples):
@@ -116,17 +117,17 @@ class ResnetBlock2D(nn.Module):
 
     def forward(self, x, temb_act=None, frames_per_clip=1):
         """x [N,H,W,Cin]; temb_act = SiLU(time embedding) as bf16 [B, temb_channels] (one row per clip)."""
-        N = x.shape[0]
+        N, H, W, _ = x.shape
         x_skip, h = ops.fork(x)
         h = run_group_norm(self.norm1, h, True, N)
         rowbias = None
         if temb_act is not None and self.time_emb_proj is not None:
             rowbias = run_linear(self.time_emb_proj, temb_act, out_fp32=True)
-        h = run_conv(self.conv1, h, rowbias=rowbias, rb_div=frames_per_clip)
+        h = run_conv(self.conv1, h, rowbias=rowbias, rb_div=frames_per_clip, stats_rows=H * W)   # -> norm2
         h = run_group_norm(self.norm2, h, True, N)
         if self.conv_shortcut is not None:
             x_skip = run_conv(self.conv_shortcut, x_skip, pads=(0, 0, 0, 0))
-        return run_conv(self.conv2, h, residual=x_skip)
+        return run_conv(self.conv2, h, residual=x_skip, stats_rows=H * W)   # -> the GroupNorm of whatever comes next
 
 
 class TemporalConvLayer(nn.Module):
@@ -163,8 +164,8 @@ class TemporalConvLayer(nn.Module):
                 h = ops.dropout(h, seq[2].p)
             h = h.view(B, num_frames, H * W, h.shape[-1])
             res = identity.view(B, num_frames, H * W, C) if i == 3 else None
-            h = run_conv(seq[-1], h, residual=res, pads=(1, 1, 0, 0))
-            h = h.view(N, H, W, -1)
+            h = run_conv(seq[-1], h, residual=res, pads=(1, 1, 0, 0), stats_rows=H * W)   # frame = (b, f): rows of one f-line
+            h = ops.view(h, N, H, W, -1)
         return h
 
 
@@ -178,7 +179,8 @@ class Downsample2D(nn.Module):
 
     def forward(self, x):
         pads = (1, 1, 1, 1) if self.padding == 1 else (0, 1, 0, 1)  # the VAE pads (0,1,0,1) then convolves unpadded
-        return run_conv(self.conv, x, stride=2, pads=pads)
+        Ho, Wo = (x.shape[1] + pads[0] + pads[1] - 3) // 2 + 1, (x.shape[2] + pads[2] + pads[3] - 3) // 2 + 1
+        return run_conv(self.conv, x, stride=2, pads=pads, stats_rows=Ho * Wo)
 
 
 class Upsample2D(nn.Module):
@@ -191,7 +193,7 @@ class Upsample2D(nn.Module):
     def forward(self, x, output_size=None):
         N, H, W, C = x.shape
         size = (2 * H, 2 * W) if output_size is None else tuple(output_size)
-        return run_conv(self.conv, ops.upsample_nearest(x, size))
+        return run_conv(self.conv, ops.upsample_nearest(x, size), stats_rows=size[0] * size[1])
 
 
 # ------------------------------------------------------------------------------------------------ attention family
@@ -335,7 +337,7 @@ class Transformer2DModel(nn.Module):
                                  attn.heads).view(B * Lq, -1)
 
         h = self.transformer_blocks[0](h, encoder_hidden_states, attend, attend_cross)
-        out = run_linear(self.proj_out, h, residual=res.view(N * H * W, C)).view(N, H, W, C)
+        out = ops.view(run_linear(self.proj_out, h, residual=res.view(N * H * W, C), stats_rows=H * W), N, H, W, C)
         return SampleOutput(sample=out) if return_dict else (out,)
 
 
@@ -371,5 +373,5 @@ class TransformerTemporalModel(nn.Module):
             return ops.temporal_attention(q, k, v, attn.heads, B, num_frames, H * W)
 
         h = self.transformer_blocks[0](h, None, attend)
-        out = run_linear(self.proj_out, h, residual=res.view(N * H * W, C)).view(N, H, W, C)
+        out = ops.view(run_linear(self.proj_out, h, residual=res.view(N * H * W, C), stats_rows=H * W), N, H, W, C)
         return SampleOutput(sample=out) if return_dict else (out,)

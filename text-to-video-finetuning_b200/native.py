@@ -52,7 +52,8 @@ def build(force=False, verbose=False):
 class Epilogue(ctypes.Structure):
     _fields_ = [("bias", ctypes.c_void_p), ("rowbias", ctypes.c_void_p), ("residual", ctypes.c_void_p),
                 ("alpha", ctypes.c_float), ("out_fp32", ctypes.c_int32), ("rowbias_div", ctypes.c_int32),
-                ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_int64)]
+                ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_int64),
+                ("stats", ctypes.c_void_p), ("stats_ld", ctypes.c_int64), ("stats_rows", ctypes.c_int32), ("pad_", ctypes.c_int32)]
 
 
 class Mat(ctypes.Structure):
@@ -61,7 +62,7 @@ class Mat(ctypes.Structure):
 
 
 EXPORTS = [
-    "t2v_version", "t2v_last_error", "t2v_launch_count", "t2v_conv_fwd", "t2v_conv_dgrad", "t2v_conv_workspace_bytes", "t2v_conv_wgrad", "t2v_bgemm", "t2v_flash_attn_fwd", "t2v_flash_attn_bwd_splits", "t2v_flash_attn_bwd",
+    "t2v_version", "t2v_last_error", "t2v_launch_count", "t2v_stream_capture_id", "t2v_channel_stats", "t2v_conv_fwd", "t2v_conv_dgrad", "t2v_conv_workspace_bytes", "t2v_conv_wgrad", "t2v_bgemm", "t2v_flash_attn_fwd", "t2v_flash_attn_bwd_splits", "t2v_flash_attn_bwd",
     "t2v_groupnorm_workspace_bytes", "t2v_groupnorm_fwd", "t2v_groupnorm_bwd", "t2v_layernorm_fwd", "t2v_layernorm_bwd",
     "t2v_latents_to_nhwc8", "t2v_nhwc8_to_latents", "t2v_mse_loss", "t2v_vae_sample", "t2v_geglu_fwd", "t2v_geglu_bwd", "t2v_silu_f32_to_bf16",
     "t2v_silu_bwd_f32", "t2v_silu_bf16", "t2v_silu_bf16_bwd", "t2v_add_bf16", "t2v_add_f32", "t2v_dropout_scale_add", "t2v_scale_bf16", "t2v_cast_f32_bf16", "t2v_sqnorm_chunks", "t2v_adamw_prepare", "t2v_adamw_chunks", "t2v_counter_add", "t2v_upsample_nearest_fwd",
@@ -75,6 +76,9 @@ def _declare(lib):
     lib.t2v_version.restype = i32
     lib.t2v_last_error.restype = ctypes.c_char_p
     lib.t2v_launch_count.restype = i64
+    lib.t2v_stream_capture_id.restype = i64
+    lib.t2v_stream_capture_id.argtypes = [vp]
+    lib.t2v_channel_stats.argtypes = [vp, vp, i32, i64, i32, i64, vp]
     conv_args = [vp, vp, vp] + [i32] * 12
     lib.t2v_conv_fwd.argtypes = conv_args + [ctypes.POINTER(Epilogue), vp]
     lib.t2v_conv_dgrad.argtypes = conv_args + [ctypes.POINTER(Epilogue), vp]
@@ -88,7 +92,7 @@ def _declare(lib):
     lib.t2v_flash_attn_bwd_splits.argtypes = [i32] * 4
     lib.t2v_groupnorm_workspace_bytes.restype = i64
     lib.t2v_groupnorm_workspace_bytes.argtypes = [i32, i64, i32]
-    lib.t2v_groupnorm_fwd.argtypes = [vp] * 7 + [i32, i64, i32, i32, f32, i32, vp]
+    lib.t2v_groupnorm_fwd.argtypes = [vp] * 7 + [i32, i64, vp, i64, i32, vp, i32, i64, i32, i32, f32, i32, vp]
     lib.t2v_groupnorm_bwd.argtypes = [vp] * 10 + [i32, i64, i32, i32, i32, vp]
     lib.t2v_layernorm_fwd.argtypes = [vp] * 5 + [i64, i32, f32, vp]
     lib.t2v_layernorm_bwd.argtypes = [vp] * 8 + [i64, i32, vp]

@@ -121,10 +121,24 @@ class _Fork(Function):
         return acc, None
 
 
+def carry(dst, src):
+    """GroupNorm input statistics travel with the activation as a Python attribute (`_t2v_stats`: list of fp32 tensors
+    [frames, Ck, 2] covering consecutive channel ranges, filled by the epilogue of the GEMM that produced the activation).
+    Views and identity ops hand them on with this helper; anything that changes values simply does not."""
+    st = getattr(src, "_t2v_stats", None)
+    if st is not None:
+        dst._t2v_stats = st
+    return dst
+
+
+def view(x, *shape):
+    return carry(x.view(*shape), x)
+
+
 def fork(x, n=2):
     if not x.requires_grad:
         return (x,) * n
-    return _Fork.apply(x, n)
+    return tuple(carry(y, x) for y in _Fork.apply(x, n))
 
 
 # ------------------------------------------------------------------------------------------- side stream for weight gradients
@@ -194,7 +208,7 @@ class _GradMark(Function):
 
 
 def grad_mark(x, hook, key):
-    return _GradMark.apply(x, hook, key) if hook is not None and x.requires_grad else x
+    return carry(_GradMark.apply(x, hook, key), x) if hook is not None and x.requires_grad else x
 
 
 # ---------------------------------------------------------------------------------------------------- conv / linear
@@ -202,7 +216,8 @@ class _Conv(Function):
     """y = conv(x, W) + bias + rowbias[n // rb_div] + residual on the tcgen05 implicit-GEMM kernel."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, rowbias, residual, stride, pads, rb_div, out_fp32, cin_pad, cout_pad, alpha, anchor=None):
+    def forward(ctx, x, weight, bias, rowbias, residual, stride, pads, rb_div, out_fp32, cin_pad, cout_pad, alpha, anchor=None,
+                stats_rows=0, stats_out=None):
         # `anchor`: a trainable tensor standing in for a FusedWeight (not a tensor) so that autograd still schedules
         # this node when x itself needs no gradient (cross-attention K|V projection of the text states)
         w = weight_bf16(weight)
@@ -216,7 +231,15 @@ class _Conv(Function):
         b = _f32(bias)
         if b is not None and cout_pad:
             b = torch.cat([b, b.new_zeros(cout_pad)])
-        y = prims.conv_fwd(x, w, b, rowbias, residual, stride, pads, alpha, out_fp32, rb_div)
+        stats = None
+        if stats_rows and stats_out is not None and not out_fp32 and not cout_pad:
+            # GroupNorm statistics of y from the GEMM epilogue: one (sum, sum of squares) per frame and channel
+            Ho, Wo = prims.out_hw(x.shape[1], x.shape[2], w.shape[1], w.shape[2], stride, pads)
+            rows = x.shape[0] * Ho * Wo
+            if rows % stats_rows == 0:
+                stats = prims.stats_alloc(rows // stats_rows, w.shape[0], x.device)
+                stats_out.append(stats)
+        y = prims.conv_fwd(x, w, b, rowbias, residual, stride, pads, alpha, out_fp32, rb_div, stats=stats, stats_rows=stats_rows if stats is not None else 0)
         ctx.save_for_backward(x, w)
         ctx.weight, ctx.bias = weight, bias
         ctx.meta = (stride, pads, rb_div, cin_pad, cout_pad, rowbias.shape if rowbias is not None else None,
@@ -268,32 +291,52 @@ class _Conv(Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = prims.conv_dgrad(dy, w, (x.shape[1], x.shape[2]), stride, pads)
-        return dx, None, None, d_rowbias, d_res, None, None, None, None, None, None, None, None
+        return dx, None, None, d_rowbias, d_res, None, None, None, None, None, None, None, None, None, None
+
+
+def _with_stats(y, holder):
+    if holder:
+        y._t2v_stats = [holder[0]]
+    return y
 
 
 def conv(x, weight, bias=None, rowbias=None, residual=None, stride=1, pads=(1, 1, 1, 1), rb_div=1, out_fp32=False,
-         cin_pad=0, cout_pad=0, alpha=1.0):
-    return _Conv.apply(x, weight, bias, rowbias, residual, stride, tuple(pads), rb_div, out_fp32, cin_pad, cout_pad, float(alpha))
+         cin_pad=0, cout_pad=0, alpha=1.0, stats_rows=0):
+    """stats_rows > 0: also emit the per-(frame, channel) GroupNorm statistics of the output from the GEMM epilogue
+    (stats_rows = output rows per frame); they ride on the returned tensor (see `carry`)."""
+    holder = [] if stats_rows else None
+    y = _Conv.apply(x, weight, bias, rowbias, residual, stride, tuple(pads), rb_div, out_fp32, cin_pad, cout_pad, float(alpha), None,
+                    int(stats_rows), holder)
+    return _with_stats(y, holder)
 
 
-def linear(x, weight, bias=None, residual=None, out_fp32=False, alpha=1.0):
+def linear(x, weight, bias=None, residual=None, out_fp32=False, alpha=1.0, stats_rows=0):
     """x [rows, in] -> [rows, out] through the same kernel (a 1x1 convolution over a rows x 1 image)."""
     rows, cin = x.shape
     res4 = residual.view(1, 1, rows, -1) if residual is not None else None
     anchor = weight.params[0] if isinstance(weight, FusedWeight) and weight.requires_grad else None
-    y = _Conv.apply(x.view(1, 1, rows, cin), weight, bias, None, res4, 1, (0, 0, 0, 0), 1, out_fp32, 0, 0, float(alpha), anchor)
-    return y.view(rows, -1)
+    holder = [] if stats_rows else None
+    y = _Conv.apply(x.view(1, 1, rows, cin), weight, bias, None, res4, 1, (0, 0, 0, 0), 1, out_fp32, 0, 0, float(alpha), anchor,
+                    int(stats_rows), holder)
+    return _with_stats(y.view(rows, -1), holder)
 
 
 # ---------------------------------------------------------------------------------------------------- norms
 class _GroupNorm(Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, groups, eps, silu, samples):
+    def forward(ctx, x, gamma, beta, groups, eps, silu, samples, stats):
         shape = x.shape
         C = shape[-1]
         x3 = x.view(samples, -1, C)
         g32, b32 = _f32(gamma), _f32(beta)
-        y, stat, ab = prims.groupnorm_fwd(x3, g32, b32, groups, eps, silu)
+        fps = 1
+        if stats is not None:   # per-frame sums from the producer's epilogue; a sample spans fps frames (per-clip norms: F)
+            frames = stats[0].shape[0]
+            ok = (len(stats) <= 2 and frames % samples == 0 and sum(t.shape[1] for t in stats) == C
+                  and all(t.shape[0] == frames and t.device == x.device for t in stats))
+            fps = frames // samples if ok else 1
+            stats = stats if ok else None
+        y, stat, ab = prims.groupnorm_fwd(x3, g32, b32, groups, eps, silu, stats, fps)
         ctx.save_for_backward(x3, g32, stat, ab)
         ctx.gamma, ctx.beta = gamma, beta
         ctx.meta = (groups, silu, shape)
@@ -306,12 +349,17 @@ class _GroupNorm(Function):
         dgamma = grad_vec(ctx.gamma) if ctx.gamma.requires_grad else None
         dbeta = grad_vec(ctx.beta) if ctx.beta.requires_grad else None
         dx = prims.groupnorm_bwd(_cont(dy).view(x3.shape), x3, g32, stat, ab, groups, silu, None, dgamma, dbeta)
-        return dx.view(shape), None, None, None, None, None, None
+        return dx.view(shape), None, None, None, None, None, None, None
+
+
+_STATS_ENABLED = not os.environ.get("T2V_NO_EPILOGUE_STATS")   # A/B switch: GroupNorm computes its own sums
 
 
 def group_norm(x, gamma, beta, groups, eps, silu, samples):
-    """x [..., C] with `samples` independent normalisation samples (frames or clips) along the leading dims."""
-    return _GroupNorm.apply(x, gamma, beta, groups, eps, silu, samples)
+    """x [..., C] with `samples` independent normalisation samples (frames or clips) along the leading dims.  When the
+    producer of x left its per-frame channel sums on the tensor (`carry`), the statistics pass is skipped."""
+    stats = getattr(x, "_t2v_stats", None) if _STATS_ENABLED else None
+    return _GroupNorm.apply(x, gamma, beta, groups, eps, silu, samples, stats)
 
 
 class _LayerNorm(Function):
@@ -470,7 +518,11 @@ class _Concat(Function):
 
 
 def concat_channels(a, b):
-    return _Concat.apply(a, b)
+    out = _Concat.apply(a, b)
+    sa, sb = getattr(a, "_t2v_stats", None), getattr(b, "_t2v_stats", None)
+    if sa is not None and sb is not None and len(sa) == 1 and len(sb) == 1:
+        out._t2v_stats = [sa[0], sb[0]]   # channel ranges [0, Ca) and [Ca, Ca + Cb)
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------- attention

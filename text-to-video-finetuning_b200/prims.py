@@ -47,8 +47,11 @@ def _conv_scratch(dgrad, N, H, W, Ci, Co, KH, KW, stride, pads, device):
     return torch.empty(n // 4, device=device, dtype=torch.float32), n
 
 
-def conv_fwd(x, w, bias=None, rowbias=None, residual=None, stride=1, pads=(0, 0, 0, 0), alpha=1.0, out_fp32=False, rowbias_div=1):
-    """x [N,H,W,Ci] bf16, w [Co,KH,KW,Ci] bf16 -> y [N,Ho,Wo,Co]; y = alpha*conv + bias[c] + rowbias[n,c] + residual."""
+def conv_fwd(x, w, bias=None, rowbias=None, residual=None, stride=1, pads=(0, 0, 0, 0), alpha=1.0, out_fp32=False, rowbias_div=1,
+             stats=None, stats_rows=0):
+    """x [N,H,W,Ci] bf16, w [Co,KH,KW,Ci] bf16 -> y [N,Ho,Wo,Co]; y = alpha*conv + bias[c] + rowbias[n,c] + residual.
+    stats: zeroed fp32 [frames, Co, 2] to receive the per-(frame, channel) sum / sum of squares of y (GroupNorm input
+    statistics from the GEMM epilogue), stats_rows = output rows per frame."""
     _chk_bf16(x, w, residual)
     _chk_f32(bias, rowbias)
     N, H, W, Ci = x.shape
@@ -59,7 +62,11 @@ def conv_fwd(x, w, bias=None, rowbias=None, residual=None, stride=1, pads=(0, 0,
     ws, ws_bytes = _conv_scratch(0, N, H, W, Ci, Co, KH, KW, stride, pads, x.device)
     epi = native.Epilogue(bias.data_ptr() if bias is not None else None, rowbias.data_ptr() if rowbias is not None else None,
                           residual.data_ptr() if residual is not None else None, float(alpha), int(out_fp32), int(rowbias_div),
-                          ws.data_ptr() if ws is not None else None, ws_bytes)
+                          ws.data_ptr() if ws is not None else None, ws_bytes,
+                          stats.data_ptr() if stats is not None else None, Co, int(stats_rows), 0)
+    if stats is not None:
+        _chk_f32(stats)
+        assert stats.shape[1:] == (Co, 2) and stats.shape[0] * stats_rows == N * Ho * Wo, (stats.shape, stats_rows, (N, Ho, Wo, Co))
     native.check(native.lib().t2v_conv_fwd(_p(x), _p(w), _p(y), N, H, W, Ci, Co, KH, KW, stride, *pads, ctypes.byref(epi), _stream()))
     return y
 
@@ -138,30 +145,75 @@ def flash_attn_bwd(q, k, v, o, do, lse, heads, dq, dk, dv):
 
 
 # ---------------------------------------------------------------------------------------------- norms
-_gn_ws = {}
+class _ZeroPool:
+    """Zero-initialised fp32 scratch for red.add targets (GroupNorm statistics / gradient sums): slices of 4 MB chunks, one
+    memset per chunk instead of one per call.  A slice is handed out once; a chunk dies with its last slice.  A chunk never
+    crosses a CUDA-graph capture boundary (its memset belongs to exactly one graph, or to none)."""
+    CHUNK = 1 << 20
+
+    def __init__(self):
+        self.state = {}   # device -> [chunk, pos, capture id]
+
+    def take(self, n, device):
+        n = (n + 63) // 64 * 64
+        if n > self.CHUNK:
+            return torch.zeros(n, device=device, dtype=torch.float32)
+        cap = native.lib().t2v_stream_capture_id(_stream()) if device.type == "cuda" else 0
+        st = self.state.get(device)
+        if st is None or st[2] != cap or st[1] + n > self.CHUNK:
+            st = self.state[device] = [torch.zeros(self.CHUNK, device=device, dtype=torch.float32), 0, cap]
+        out = st[0][st[1]:st[1] + n]
+        st[1] += n
+        return out
 
 
-def groupnorm_ws(S, P, C, device):
-    """The GroupNorm kernels want zeroed scratch and hand it back zeroed: one buffer per device, grown on demand."""
-    n = (native.lib().t2v_groupnorm_workspace_bytes(S, P, C) + 3) // 4
-    ws = _gn_ws.get(device)
-    if ws is None or ws.numel() < n:
-        ws = torch.zeros(max(n, 1 << 16), device=device, dtype=torch.float32)
-        _gn_ws[device] = ws
-    return ws
+_zero_pool = _ZeroPool()
 
 
-def groupnorm_fwd(x, gamma, beta, G, eps, silu):
-    """x [S,P,C] bf16 -> y, stat [S,G,2], ab [S,C,2]."""
+def zeros_f32(shape, device):
+    n = 1
+    for d in shape:
+        n *= d
+    return _zero_pool.take(n, torch.device(device))[:n].view(shape)
+
+
+def stats_alloc(frames, C, device):
+    """Zeroed [frames, C, 2] buffer for epilogue statistics (conv_fwd(stats=...))."""
+    return zeros_f32((frames, C, 2), device)
+
+
+def channel_stats(x):
+    """x [S,P,C] bf16 -> per-sample, per-channel (sum, sum of squares) [S,C,2] fp32: the statistics pass on its own."""
+    _chk_bf16(x)
+    S, P, C = x.shape
+    st = stats_alloc(S, C, x.device)
+    native.check(native.lib().t2v_channel_stats(_p(x), _p(st), S, P, C, C, _stream()))
+    return st
+
+
+def groupnorm_fwd(x, gamma, beta, G, eps, silu, stats=None, fps=1):
+    """x [S,P,C] bf16 -> y, stat [S,G,2], ab [S,C,2].  stats: None (the kernel computes the sums itself) or a list of one or
+    two fp32 tensors [S*fps, Ck, 2] with the per-frame sums of consecutive channel ranges (sum Ck == C) as produced by
+    conv_fwd(stats=...); fps = frames per normalisation sample."""
     _chk_bf16(x)
     _chk_f32(gamma, beta)
     S, P, C = x.shape
     y = torch.empty_like(x)
     stat = torch.empty((S, G, 2), device=x.device, dtype=torch.float32)
     ab = torch.empty((S, C, 2), device=x.device, dtype=torch.float32)
-    ws = groupnorm_ws(S, P, C, x.device)
-    native.check(native.lib().t2v_groupnorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(stat), _p(ab), _p(ws), S, P, C, G, float(eps),
-                                                int(silu), _stream()))
+    if stats:
+        s0 = stats[0]
+        s1 = stats[1] if len(stats) > 1 else None
+        _chk_f32(s0, s1)
+        C0 = s0.shape[1]
+        assert s0.shape[0] == S * fps and C0 + (s1.shape[1] if s1 is not None else 0) == C, (s0.shape, S, fps, C)
+        native.check(native.lib().t2v_groupnorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(stat), _p(ab), _p(s0), C0, C0, _p(s1),
+                                                    s1.shape[1] if s1 is not None else 0, fps, _p(None), S, P, C, G, float(eps), int(silu),
+                                                    _stream()))
+    else:
+        ws = zeros_f32((S, C, 2), x.device)
+        native.check(native.lib().t2v_groupnorm_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(stat), _p(ab), _p(None), 0, 0, _p(None), 0, 1,
+                                                    _p(ws), S, P, C, G, float(eps), int(silu), _stream()))
     return y, stat, ab
 
 
@@ -169,7 +221,7 @@ def groupnorm_bwd(dy, x, gamma, stat, ab, G, silu, add=None, dgamma=None, dbeta=
     _chk_bf16(dy, x, add)
     S, P, C = x.shape
     dx = torch.empty_like(x)
-    ws = groupnorm_ws(S, P, C, x.device)
+    ws = zeros_f32((S, C, 2), x.device)
     native.check(native.lib().t2v_groupnorm_bwd(_p(dy), _p(x), _p(gamma), _p(stat), _p(ab), _p(add), _p(dx), _p(dgamma), _p(dbeta),
                                                 _p(ws), S, P, C, G, int(silu), _stream()))
     return dx

@@ -130,7 +130,7 @@ def _finish_branch(m, u_fn, base):
     return ops.dropout_scale_add(u_fn(None, 1.0), base, m.dropout.p, m.scale)
 
 
-def lora_linear_forward(m, x, residual=None, out_fp32=False):
+def lora_linear_forward(m, x, residual=None, out_fp32=False, stats_rows=0):
     if out_fp32:  # only the tiny per-clip time_emb_proj rows ask for fp32: widen the bf16 result (a [B, C] tensor)
         return lora_linear_forward(m, x, residual, False).float()
     x1, x2 = ops.fork(x)
@@ -138,10 +138,12 @@ def lora_linear_forward(m, x, residual=None, out_fp32=False):
     z = ops.linear(x2, m.lora_down.weight)
     if isinstance(m.selector, nn.Linear):
         z = ops.linear(z, m.selector.weight)
-    return _finish_branch(m, lambda res, alpha: ops.linear(z, m.lora_up.weight, None, res, alpha=alpha), base)
+    # GroupNorm statistics ride on the last GEMM of the wrapper (the up-projection, whose epilogue adds the base output)
+    return _finish_branch(m, lambda res, alpha: ops.linear(z, m.lora_up.weight, None, res, alpha=alpha,
+                                                           stats_rows=stats_rows if res is not None else 0), base)
 
 
-def lora_conv_forward(m, x, rowbias=None, residual=None, stride=None, pads=None, rb_div=1, cin_pad=0, cout_pad=0):
+def lora_conv_forward(m, x, rowbias=None, residual=None, stride=None, pads=None, rb_div=1, cin_pad=0, cout_pad=0, stats_rows=0):
     conv = m.conv
     if stride is None:
         stride = conv.stride[0]
@@ -153,7 +155,8 @@ def lora_conv_forward(m, x, rowbias=None, residual=None, stride=None, pads=None,
     z = ops.conv(x2, m.lora_down.weight, None, None, None, stride, pads)
     if not isinstance(m.selector, nn.Identity):
         z = ops.conv(z, m.selector.weight, pads=(0, 0, 0, 0))
-    return _finish_branch(m, lambda res, alpha: ops.conv(z, m.lora_up.weight, None, None, res, 1, (0, 0, 0, 0), alpha=alpha), base)
+    return _finish_branch(m, lambda res, alpha: ops.conv(z, m.lora_up.weight, None, None, res, 1, (0, 0, 0, 0), alpha=alpha,
+                                                         stats_rows=stats_rows if res is not None else 0), base)
 
 
 # ------------------------------------------------------------------------------------------------ module search
