@@ -288,8 +288,8 @@ def test_conv_epilogue_statistics(case):
     yf = y.float().view(frames, srows, Co)
     want = torch.stack([yf.sum(1), (yf * yf).sum(1)], dim=-1)
     # the epilogue sums the fp32 values before bf16 rounding: agreement is at bf16 rounding level of the SUM, not the element
-    close(stats[..., 0], want[..., 0], 2e-3, "sum")
-    close(stats[..., 1], want[..., 1], 2e-3, "sum of squares")
+    close(stats[..., 0], want[..., 0], 5e-3, "sum")
+    close(stats[..., 1], want[..., 1], 5e-3, "sum of squares")
     # and a GroupNorm fed with them equals a GroupNorm that computes its own sums
     gamma = 1 + 0.2 * torch.randn(Co, device=DEV, generator=g)
     beta = 0.1 * torch.randn(Co, device=DEV, generator=g)

@@ -68,21 +68,6 @@ __device__ __forceinline__ void issue_boxes(const TmaOperand& op, const int32_t*
     }
 }
 
-// One step of the transposing warp reduction used for the GroupNorm statistics: 2*CNT per-lane partial column sums become
-// CNT, lanes XOR apart exchange the half they do not keep.  After the steps (16,16)(8,8)(4,4)(2,2)(1,1) lane L holds in s[0]
-// the sum over all 32 lanes (rows) of column L; after (16,8)(8,4)(4,2)(2,1) it holds in s[0], s[1] the sums over its own
-// 16-lane half of columns 2*(L%16) and 2*(L%16)+1.
-template <int CNT, int XOR>
-__device__ __forceinline__ void xreduce_step(float (&s)[32], uint32_t lane) {
-    const bool up = (lane & XOR) != 0;
-#pragma unroll
-    for (int j = 0; j < CNT; ++j) {
-        const float send = up ? s[j] : s[j + CNT];
-        const float keep = up ? s[j + CNT] : s[j];
-        s[j] = keep + __shfl_xor_sync(0xffffffffu, send, XOR);
-    }
-}
-
 // Epilogue of one CTA (warps 2..9).  mh == 1: the two groups of four warps split the accumulator columns; mh == 2: group g
 // drains row half g.  Within a group warp w owns TMEM lanes 32*(w%4)..+31, i.e. thread <-> output row.  Output rows are
 // strided in global memory, so every 32-column chunk goes through a per-warp swizzled staging tile and is moved with
@@ -138,9 +123,11 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
         // GroupNorm statistics: frame of this lane's segment (taken from the segment's first row, which is in bounds
         // whenever any row of the segment is)
         int64_t st_off = 0;
+        uint32_t okmask = 0;
         if (has_stats) {
             const int32_t fr = (gw * p.st_cw + gh * p.st_ch + gn * p.st_cn) / p.st_div;
             st_off = int64_t(__shfl_sync(0xffffffffu, fr, lane & ~uint32_t(p.st_seg - 1))) * p.st_ld;
+            okmask = __ballot_sync(0xffffffffu, row_ok);
         }
         const uint32_t as = p.nacc == 2 ? (it & 1u) : 0u;
         const uint32_t aphase = p.nacc == 2 ? ((it >> 1) & 1u) : (it & 1u);
@@ -204,31 +191,6 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
                     }
                     __syncwarp();
                 }
-                if (has_stats) {   // per-(frame, channel) sum and sum of squares of the final fp32 values of this chunk
-                    float s1[32], s2[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float t = row_ok ? v[j] : 0.f;
-                        s1[j] = t;
-                        s2[j] = t * t;
-                    }
-                    float* sp = p.stats + (st_off + col) * 2;
-                    if (p.st_seg == 32) {
-                        xreduce_step<16, 16>(s1, lane); xreduce_step<16, 16>(s2, lane);
-                        xreduce_step<8, 8>(s1, lane);   xreduce_step<8, 8>(s2, lane);
-                        xreduce_step<4, 4>(s1, lane);   xreduce_step<4, 4>(s2, lane);
-                        xreduce_step<2, 2>(s1, lane);   xreduce_step<2, 2>(s2, lane);
-                        xreduce_step<1, 1>(s1, lane);   xreduce_step<1, 1>(s2, lane);
-                        if (static_cast<int32_t>(lane) < cvalid) red_add_f32x2(sp + 2 * lane, s1[0], s2[0]);
-                    } else {
-                        xreduce_step<16, 8>(s1, lane);  xreduce_step<16, 8>(s2, lane);
-                        xreduce_step<8, 4>(s1, lane);   xreduce_step<8, 4>(s2, lane);
-                        xreduce_step<4, 2>(s1, lane);   xreduce_step<4, 2>(s2, lane);
-                        xreduce_step<2, 1>(s1, lane);   xreduce_step<2, 1>(s2, lane);
-                        const int c = 2 * (lane & 15);
-                        if (c < cvalid) red_add_f32x4(sp + 2 * c, s1[0], s2[0], s1[1], s2[1]);
-                    }
-                }
                 // own row -> staging
                 if (ESZ == 2) {
 #pragma unroll
@@ -246,6 +208,32 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
                         *reinterpret_cast<float4*>(stg + phys(lane, j, 8)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
                 __syncwarp();
+                if (ESZ == 2 && has_stats) {
+                    // GroupNorm statistics of the tile just staged (the bf16 values the consumer will read): lanes 0-15 walk
+                    // rows 0-15, lanes 16-31 rows 16-31 (staggered by one row so the two halves hit different banks), each lane
+                    // owns the column pair (2c, 2c+1), c = lane % 16.  16-row segments: every half is one frame; 32-row
+                    // segments: the halves are combined with one shuffle.
+                    const uint32_t half = lane >> 4, cw = lane & 15u;
+                    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int r = half ? 16 + ((i + 1) & 15) : i;
+                        const uint32_t w = *reinterpret_cast<const uint32_t*>(stg + phys(r, int(cw >> 2), 4) + (cw & 3u) * 4u);
+                        if ((okmask >> r) & 1u) {
+                            const float lo = bf16_lo(w), hi = bf16_hi(w);
+                            s0 += lo; q0 += lo * lo;
+                            s1 += hi; q1 += hi * hi;
+                        }
+                    }
+                    if (p.st_seg == 32) {
+                        s0 += __shfl_xor_sync(0xffffffffu, s0, 16); q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+                    }
+                    // a segment without a valid row has no frame (its offset is meaningless): it contributes nothing
+                    const bool any_row = p.st_seg == 16 ? ((okmask >> (half * 16u)) & 0xFFFFu) != 0u : okmask != 0u;
+                    if (any_row && (p.st_seg == 16 || half == 0) && int(2 * cw) < cvalid)
+                        red_add_f32x4(p.stats + (st_off + col + 2 * cw) * 2, s0, q0, s1, q1);
+                }
                 // staging -> global: 16 bytes per lane, whole row segments
                 const int nval = cvalid - sj * EPC;  // valid elements in this lane's chunk
 #pragma unroll
