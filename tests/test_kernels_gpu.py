@@ -268,6 +268,10 @@ def test_attention_composite(Nb, Lq, Lk, heads, D):
     ((1, 16, 16, 640), 640, (3, 1), 1, (1, 1, 0, 0), 16, False, "temporal conv at the 4x4 level"),
     ((16, 32, 32, 64), 128, (3, 3), 2, (1, 1, 1, 1), 256, False, "stride-2 downsample conv"),
     ((4, 12, 20, 64), 96, (3, 3), 1, (1, 1, 1, 1), 240, False, "ragged map (40x72-like): falls back to the statistics pass"),
+    ((16, 8, 8, 64), 128, (3, 3), 1, (1, 1, 1, 1), 4 * 64, True, "per-clip statistics from a per-frame conv (4 frames per sample)"),
+    ((16, 4, 4, 128), 256, (3, 3), 1, (1, 1, 1, 1), 16 * 16, True, "per-clip statistics at the 4x4 level (one sample)"),
+    ((16, 32, 32, 8), 320, (3, 3), 1, (1, 1, 1, 1), 16 * 1024, False, "conv_in -> transformer_in (per clip, 8 input channels)"),
+    ((1, 1, 16384, 320), 320, (1, 1), 1, (0, 0, 0, 0), 16384, True, "linear, one sample over all rows"),
 ])
 def test_conv_epilogue_statistics(case):
     """T2VEpilogue.stats: the per-(frame, channel) sums a GEMM epilogue (or its split-K finishing pass, or the fallback

@@ -221,24 +221,28 @@ void apply_fwd_splits(GemmParams& p, int splits, int kb_total) {
 // cannot do it (the caller then runs the standalone statistics pass over the finished output).
 bool plan_epilogue_stats(GemmParams& p, const T2VEpilogue* e, int Wo, int Ho, int N) {
     if (!e || !e->stats || e->stats_rows <= 0) return false;
-    const int64_t pf = e->stats_rows;
+    const int64_t pf = e->stats_rows;     // output rows (flattened [N][Ho][Wo]) per statistics sample
+    const int64_t frame = int64_t(Wo) * Ho;
     int cw = 0, ch = 0, cn = 0, div = 1;
-    int64_t run;   // accumulator rows (in tile row order: w fastest, then h, then n) that share a frame
-    if (pf == int64_t(Wo) * Ho) {
-        cn = 1;
-        run = int64_t(p.bw) * p.bh;
-    } else if (pf == Wo) {
-        ch = 1; cn = Ho;
-        run = p.bw;
-    } else if (Ho == 1 && N == 1 && Wo % pf == 0) {
-        cw = 1; div = int(pf);
-        run = p.bh == 1 && p.bn == 1 ? pf : 0;
-    } else {
-        return false;
-    }
+    // does every aligned run of `seg` accumulator rows (tile row order: w fastest, then h, then n) share a sample?
+    auto pick_seg = [&](auto&& ok) { return ok(32) ? 32 : (ok(16) ? 16 : 0); };
     int seg = 0;
-    if (run > 0 && run % 32 == 0) seg = 32;
-    else if (run > 0 && run % 16 == 0) seg = 16;
+    if (pf % frame == 0) {                // a sample is k whole images n (k = 1: per frame; k = F: per clip)
+        const int64_t k = pf / frame, fp = int64_t(p.bw) * p.bh;
+        cn = 1; div = int(k);
+        seg = pick_seg([&](int sg) {
+            if (fp % sg == 0) return true;                       // the run stays inside one image
+            if (sg % fp) return false;
+            const int64_t m = sg / fp;                           // the run covers m consecutive images of the tile
+            return k % m == 0 && p.bn % m == 0;
+        });
+    } else if (pf == Wo) {                // a sample is one h-line (temporal layout [B][F][HW]: frame = (n, h))
+        ch = 1; cn = Ho;
+        seg = pick_seg([&](int sg) { return p.bw % sg == 0; });
+    } else if (Ho == 1 && N == 1 && Wo % pf == 0) {   // token matrix: sample = row / pf
+        cw = 1; div = int(pf);
+        seg = (p.bh == 1 && p.bn == 1) ? pick_seg([&](int sg) { return pf % sg == 0; }) : 0;
+    }
     if (!seg) return false;
     p.stats = e->stats;
     p.st_ld = e->stats_ld;

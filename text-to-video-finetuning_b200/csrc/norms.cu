@@ -27,17 +27,17 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 __device__ __forceinline__ float sigmoidf_(float z) { return 1.0f / (1.0f + __expf(-z)); }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm
-// Streaming kernels with many small blocks (latency hidden by occupancy) around a tiny per-sample finalise kernel, chained
-// with programmatic dependent launch:
-//   forward    [sums]  ->  finalise  ->  apply            sums: per-(frame, channel) (sum x, sum x^2).  Usually NOT run: the
-//                                                          GEMM that produced x accumulated them in its epilogue
-//                                                          (gemm_tc.cu, EPI_STATS), so forward is one read + one write.
-//   backward   sums    ->  finalise  ->  apply            sums: per-channel (sum dz, sum dz*xhat)
-//   finalise   one block per sample: per-channel sums (over the sample's frames) -> group statistics (fp64 combine) ->
-//              per-channel coefficients.  fwd: stat [S][G][2] = (mean, rstd), ab [S][C][2] with z = a x + b;
-//              bwd: coef [S][C][4] = (pc, qc, rc, -) with dx = pc dz + qc x + rc, plus dgamma / dbeta.
-// Streaming layout: V = C/8 channel vectors; a thread owns vector tid % V (its coefficients live in registers) and pixel
-// lane tid / V; a block owns a chunk of pixels of one sample; loads are 16 bytes, several pixels in flight per thread.
+// Streaming kernels with many small blocks (<= 256 threads, several resident per SM, so the per-block latency chain
+// "sums -> group statistics -> coefficients -> pixels" of one block overlaps the streaming of its neighbours):
+//   forward    [sums] -> apply      sums: per-(sample, channel) (sum x, sum x^2).  Usually NOT run: the GEMM that produced x
+//                                   accumulated them in its epilogue (gemm_tc.cu, EPI_STATS), at the granularity this norm
+//                                   needs (per frame or per clip), so forward is ONE kernel: one read + one write of x.
+//   backward   sums   -> apply      sums: per-channel (sum dz, sum dz*xhat), red.add into zeroed scratch
+//   apply      every block finalises ITS sample's group statistics from the per-channel sums (C values from L2, fp64 group
+//              combine) and then streams its chunk of pixels; the sample's first block also writes stat / ab (forward) or
+//              dgamma / dbeta (backward).
+// Layout: V = C/8 channel vectors; a thread owns vector tid % V (its coefficients live in registers) and pixel lane
+// tid / V; loads are 16 bytes, four pixels in flight per thread.
 struct GnArgs {
     const __nv_bfloat16* x;
     const __nv_bfloat16* dy;
@@ -45,11 +45,10 @@ struct GnArgs {
     __nv_bfloat16* out;       // y (fwd) / dx (bwd)
     const float* gamma;
     const float* beta;
-    float* stat;              // [S][G][2] (mean, rstd): written by fwd finalise, read by bwd
-    float* ab;                // [S][C][2] (a, b) with z = a x + b: written by fwd finalise, read by bwd
+    float* stat;              // [S][G][2] (mean, rstd): written by fwd, read by bwd
+    float* ab;                // [S][C][2] (a, b) with z = a x + b: written by fwd, read by bwd
     float* accum;             // [S][C][2] sums (bwd; fwd when the kernel computes them itself)
-    float* coef;              // [S][C][4] bwd coefficients
-    const float* stats0;      // fwd finalise input: per-frame sums of channels [0, C0), row pitch ld0 channels
+    const float* stats0;      // fwd input: per-frame sums of channels [0, C0), row pitch ld0 channels
     const float* stats1;      // ... of channels [C0, C), row pitch ld1 (NULL when C0 == C)
     int64_t ld0, ld1;
     float* dgamma;
@@ -62,9 +61,9 @@ struct GnArgs {
 enum { GN_FWD_APPLY = 0, GN_BWD_SUMS = 1, GN_BWD_APPLY = 2, GN_FWD_SUMS = 3 };
 
 template <int MODE>
-__global__ void __launch_bounds__(512) gn_stream_kernel(const GnArgs g) {
+__global__ void __launch_bounds__(384) gn_stream_kernel(const GnArgs g) {
     pdl_sync();
-    extern __shared__ float sh[];  // sums modes: [2][C] partial sums
+    extern __shared__ float sh[];  // [2][C] per-channel sums, then [2][G] group terms
     constexpr bool kSums = MODE == GN_BWD_SUMS || MODE == GN_FWD_SUMS;
     constexpr bool kBwd = MODE == GN_BWD_SUMS || MODE == GN_BWD_APPLY;
     const int C = g.C, G = g.G, cpg = C / G;
@@ -76,21 +75,95 @@ __global__ void __launch_bounds__(512) gn_stream_kernel(const GnArgs g) {
     const int64_t p1 = min(g.P, p0 + g.chunk_pixels);
     const uint4* xs = reinterpret_cast<const uint4*>(g.x + int64_t(s) * g.P * C) + cv;
     const uint4* ds = kBwd ? reinterpret_cast<const uint4*>(g.dy + int64_t(s) * g.P * C) + cv : nullptr;
-    if (kSums) {
-        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+    float* cs = sh;              // [2][C]
+    float* t0 = sh + 2 * C;      // [G]  fwd: group mean   bwd: sum_c gamma * sum dz
+    float* t1 = t0 + G;          // [G]  fwd: group rstd   bwd: sum_c gamma * sum dz*xhat
+    float a[8], b[8], gam[8];
+
+    if (!kSums) {
+        // ---- finalise this sample's statistics (redundantly per block: C values from L2, one round trip)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gam[j] = __ldg(g.gamma + cv * 8 + j);
+        if (MODE == GN_FWD_APPLY) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b[j] = __ldg(g.beta + cv * 8 + j);
+            for (int c = threadIdx.x; c < C; c += blockDim.x) {
+                const bool first = c < g.C0;
+                const float2* src = reinterpret_cast<const float2*>(first ? g.stats0 : g.stats1) + (first ? c : c - g.C0);
+                const int64_t ld = first ? g.ld0 : g.ld1;
+                float a0 = 0.f, a1 = 0.f;
+                for (int f = 0; f < g.fps; ++f) {   // fps == 1 when the producer summed at this norm's granularity
+                    const float2 v = __ldcg(src + (int64_t(s) * g.fps + f) * ld);
+                    a0 += v.x;
+                    a1 += v.y;
+                }
+                cs[c] = a0;
+                cs[C + c] = a1;
+            }
+        } else {
+            const float2* acc = reinterpret_cast<const float2*>(g.accum + int64_t(s) * C * 2);
+            for (int c = threadIdx.x; c < C; c += blockDim.x) {
+                const float2 v = __ldcg(acc + c);
+                cs[c] = v.x;
+                cs[C + c] = v.y;
+                if (chunk == 0) {
+                    if (g.dbeta) atomicAdd(g.dbeta + c, v.x);
+                    if (g.dgamma) atomicAdd(g.dgamma + c, v.y);
+                }
+            }
+        }
+        __syncthreads();
+        {   // full warps only: one warp per group, fp64 combine of the group's channels through shuffles
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+            if (warp < nw) {
+                for (int gi = warp; gi < G; gi += nw) {
+                    double a0 = 0, a1 = 0;
+                    for (int j = lane; j < cpg; j += 32) {
+                        const int c = gi * cpg + j;
+                        const double w = MODE == GN_FWD_APPLY ? 1.0 : double(__ldg(g.gamma + c));
+                        a0 += w * cs[c];
+                        a1 += w * cs[C + c];
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                    }
+                    if (lane == 0) {
+                        if (MODE == GN_FWD_APPLY) {
+                            const double n = double(g.P) * cpg;
+                            const double m = a0 / n;
+                            double var = a1 / n - m * m;
+                            if (var < 0) var = 0;
+                            const float r = float(1.0 / sqrt(var + double(g.eps)));
+                            t0[gi] = float(m);
+                            t1[gi] = r;
+                            if (chunk == 0) {
+                                g.stat[(int64_t(s) * G + gi) * 2] = float(m);
+                                g.stat[(int64_t(s) * G + gi) * 2 + 1] = r;
+                            }
+                        } else {
+                            t0[gi] = float(a0);
+                            t1[gi] = float(a1);
+                        }
+                    }
+                }
+            }
+        }
         __syncthreads();
     }
-    // per-thread channel constants
-    float a[8], b[8];
-    if (MODE != GN_FWD_SUMS) {
-        const float4* ab4 = reinterpret_cast<const float4*>(g.ab + (int64_t(s) * C + cv * 8) * 2);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 q = __ldg(ab4 + j);
-            a[2 * j] = q.x; b[2 * j] = q.y; a[2 * j + 1] = q.z; b[2 * j + 1] = q.w;
-        }
-    }
+
     if (MODE == GN_FWD_APPLY) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = cv * 8 + j;
+            a[j] = t1[c / cpg] * gam[j];
+            b[j] = b[j] - t0[c / cpg] * a[j];
+        }
+        if (chunk == 0 && pl == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) reinterpret_cast<float2*>(g.ab)[int64_t(s) * C + cv * 8 + j] = make_float2(a[j], b[j]);
+        }
         uint4* os = reinterpret_cast<uint4*>(g.out + int64_t(s) * g.P * C) + cv;
         auto apply = [&](const uint4& qx) {
             float v[8];
@@ -103,25 +176,37 @@ __global__ void __launch_bounds__(512) gn_stream_kernel(const GnArgs g) {
             }
             return pack8(v);
         };
-        int64_t p = p0 + pl;
-        for (; p + 3 * lanes < p1; p += 4 * lanes) {
+        for (int64_t p = p0 + pl; p < p1; p += 4 * lanes) {   // four pixels in flight, the tail is predicated (not serialised)
             uint4 qx[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) qx[u] = __ldg(xs + (p + u * lanes) * V);
+            for (int u = 0; u < 4; ++u)
+                if (p + u * lanes < p1) qx[u] = __ldg(xs + (p + u * lanes) * V);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) os[(p + u * lanes) * V] = apply(qx[u]);
+            for (int u = 0; u < 4; ++u)
+                if (p + u * lanes < p1) os[(p + u * lanes) * V] = apply(qx[u]);
         }
-        for (; p < p1; p += lanes) os[p * V] = apply(__ldg(xs + p * V));
-    } else if (kSums) {
-        float mean[8], rstd[8];
-        if (MODE == GN_BWD_SUMS) {
+        return;
+    }
+
+    // backward modes and the forward sums: saved per-channel coefficients
+    float mean[8], rstd[8];
+    if (kBwd) {
+        const float4* ab4 = reinterpret_cast<const float4*>(g.ab + (int64_t(s) * C + cv * 8) * 2);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int c = cv * 8 + j;
-                mean[j] = __ldg(g.stat + (int64_t(s) * G + c / cpg) * 2);
-                rstd[j] = __ldg(g.stat + (int64_t(s) * G + c / cpg) * 2 + 1);
-            }
+        for (int j = 0; j < 4; ++j) {
+            const float4 q = __ldg(ab4 + j);
+            a[2 * j] = q.x; b[2 * j] = q.y; a[2 * j + 1] = q.z; b[2 * j + 1] = q.w;
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = cv * 8 + j;
+            mean[j] = __ldg(g.stat + (int64_t(s) * G + c / cpg) * 2);
+            rstd[j] = __ldg(g.stat + (int64_t(s) * G + c / cpg) * 2 + 1);
+        }
+    }
+    if (kSums) {
+        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+        __syncthreads();
         float acc0[8], acc1[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc0[j] = acc1[j] = 0.f;
@@ -150,18 +235,20 @@ __global__ void __launch_bounds__(512) gn_stream_kernel(const GnArgs g) {
                 }
             }
         };
-        int64_t p = p0 + pl;
-        for (; p + lanes < p1; p += 2 * lanes) {
-            uint4 qx[2], qd[2];
+        constexpr int U = MODE == GN_FWD_SUMS ? 4 : 2;
+        for (int64_t p = p0 + pl; p < p1; p += U * lanes) {
+            uint4 qx[U], qd[U];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                qx[u] = __ldg(xs + (p + u * lanes) * V);
-                qd[u] = kBwd ? __ldg(ds + (p + u * lanes) * V) : make_uint4(0, 0, 0, 0);
+            for (int u = 0; u < U; ++u) {
+                if (p + u * lanes < p1) {
+                    qx[u] = __ldg(xs + (p + u * lanes) * V);
+                    if (kBwd) qd[u] = __ldg(ds + (p + u * lanes) * V);
+                }
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) accumulate(qx[u], qd[u]);
+            for (int u = 0; u < U; ++u)
+                if (p + u * lanes < p1) accumulate(qx[u], qd[u]);
         }
-        for (; p < p1; p += lanes) accumulate(__ldg(xs + p * V), kBwd ? __ldg(ds + p * V) : make_uint4(0, 0, 0, 0));
         if (lanes == 1) {   // one pixel lane per channel vector: no contention, plain stores
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -178,139 +265,53 @@ __global__ void __launch_bounds__(512) gn_stream_kernel(const GnArgs g) {
         __syncthreads();
         float* acc = g.accum + int64_t(s) * C * 2;
         for (int c = threadIdx.x; c < C; c += blockDim.x) red_add_f32x2(acc + 2 * c, sh[c], sh[C + c]);
-    } else {  // GN_BWD_APPLY: dx = pc * dz + qc * x + rc (+ add)
-        float pc[8], qc[8], rc[8];
-        const float4* cf = reinterpret_cast<const float4*>(g.coef + (int64_t(s) * C + cv * 8) * 4);
+        return;
+    }
+
+    // GN_BWD_APPLY: dx = pc * dz + qc * x + rc (+ add)
+    float pc[8], qc[8], rc[8];
+    const float invn = 1.0f / (float(g.P) * cpg);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = cv * 8 + j;
+        const float q = -rstd[j] * rstd[j] * t1[c / cpg] * invn;
+        pc[j] = rstd[j] * gam[j];
+        qc[j] = q;
+        rc[j] = -rstd[j] * t0[c / cpg] * invn - q * mean[j];
+    }
+    uint4* os = reinterpret_cast<uint4*>(g.out + int64_t(s) * g.P * C) + cv;
+    const uint4* as = g.add ? reinterpret_cast<const uint4*>(g.add + int64_t(s) * g.P * C) + cv : nullptr;
+    auto apply = [&](const uint4& qx, const uint4& qd, const uint4& qa) {
+        float v[8], d[8], r[8];
+        unpack8(qx, v);
+        unpack8(qd, d);
+        unpack8(qa, r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float4 q = __ldg(cf + j);
-            pc[j] = q.x; qc[j] = q.y; rc[j] = q.z;
-        }
-        uint4* os = reinterpret_cast<uint4*>(g.out + int64_t(s) * g.P * C) + cv;
-        const uint4* as = g.add ? reinterpret_cast<const uint4*>(g.add + int64_t(s) * g.P * C) + cv : nullptr;
-        auto apply = [&](const uint4& qx, const uint4& qd, const uint4& qa) {
-            float v[8], d[8], r[8];
-            unpack8(qx, v);
-            unpack8(qd, d);
-            unpack8(qa, r);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float dz = d[j];
-                if (g.silu) {
-                    const float z = a[j] * v[j] + b[j];
-                    const float sg = sigmoidf_(z);
-                    dz *= sg * (1.f + z * (1.f - sg));
-                }
-                v[j] = pc[j] * dz + qc[j] * v[j] + rc[j] + r[j];
+            float dz = d[j];
+            if (g.silu) {
+                const float z = a[j] * v[j] + b[j];
+                const float sg = sigmoidf_(z);
+                dz *= sg * (1.f + z * (1.f - sg));
             }
-            return pack8(v);
-        };
-        const uint4 zero = make_uint4(0, 0, 0, 0);
-        int64_t p = p0 + pl;
-        for (; p + lanes < p1; p += 2 * lanes) {
-            uint4 qx[2], qd[2], qa[2];
+            v[j] = pc[j] * dz + qc[j] * v[j] + rc[j] + r[j];
+        }
+        return pack8(v);
+    };
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (int64_t p = p0 + pl; p < p1; p += 2 * lanes) {
+        uint4 qx[2], qd[2], qa[2];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < 2; ++u) {
+            if (p + u * lanes < p1) {
                 qx[u] = __ldg(xs + (p + u * lanes) * V);
                 qd[u] = __ldg(ds + (p + u * lanes) * V);
                 qa[u] = as ? __ldg(as + (p + u * lanes) * V) : zero;
             }
+        }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) os[(p + u * lanes) * V] = apply(qx[u], qd[u], qa[u]);
-        }
-        for (; p < p1; p += lanes) os[p * V] = apply(__ldg(xs + p * V), __ldg(ds + p * V), as ? __ldg(as + p * V) : zero);
-    }
-}
-
-// One block per sample.  MODE 0: forward (sums -> stat, ab).  MODE 1: backward (sums -> coef, dgamma, dbeta).
-template <int MODE>
-__global__ void __launch_bounds__(256) gn_finalize_kernel(const GnArgs g) {
-    pdl_sync();
-    extern __shared__ float sh[];
-    const int C = g.C, G = g.G, cpg = C / G;
-    const int s = blockIdx.x;
-    float* cs = sh;              // [2][C]
-    float* t0 = sh + 2 * C;      // [G]  fwd: group mean   bwd: sum_c gamma * sum dz
-    float* t1 = t0 + G;          // [G]  fwd: group rstd   bwd: sum_c gamma * sum dz*xhat
-    if (MODE == 0) {
-        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) cs[i] = 0.f;
-        __syncthreads();
-        // (channel, frame) pairs are independent loads: all in flight at once, combined through shared-memory atomics
-        const int total = C * g.fps;
-#pragma unroll 4
-        for (int i = threadIdx.x; i < total; i += blockDim.x) {
-            const int c = i % C, f = i / C;
-            const bool first = c < g.C0;
-            const float2* src = reinterpret_cast<const float2*>(first ? g.stats0 : g.stats1);
-            const int64_t ld = first ? g.ld0 : g.ld1;
-            const float2 v = __ldcg(src + (int64_t(s) * g.fps + f) * ld + (first ? c : c - g.C0));
-            if (g.fps == 1) {
-                cs[c] = v.x;
-                cs[C + c] = v.y;
-            } else {
-                atomicAdd(&cs[c], v.x);
-                atomicAdd(&cs[C + c], v.y);
-            }
-        }
-    } else {
-        const float2* acc = reinterpret_cast<const float2*>(g.accum + int64_t(s) * C * 2);
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            const float2 v = __ldcg(acc + c);
-            cs[c] = v.x;
-            cs[C + c] = v.y;
-            if (g.dbeta) atomicAdd(g.dbeta + c, v.x);
-            if (g.dgamma) atomicAdd(g.dgamma + c, v.y);
-        }
-    }
-    __syncthreads();
-    {   // one warp per group: fp64 combine of the group's channels through shuffles
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        for (int gi = warp; gi < G; gi += blockDim.x / 32) {
-            double a0 = 0, a1 = 0;
-            for (int j = lane; j < cpg; j += 32) {
-                const int c = gi * cpg + j;
-                const double w = MODE == 0 ? 1.0 : double(g.gamma[c]);
-                a0 += w * cs[c];
-                a1 += w * cs[C + c];
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-                a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-            }
-            if (lane == 0) {
-                if (MODE == 0) {
-                    const double n = double(g.P) * cpg;
-                    const double m = a0 / n;
-                    double var = a1 / n - m * m;
-                    if (var < 0) var = 0;
-                    const float r = float(1.0 / sqrt(var + double(g.eps)));
-                    t0[gi] = float(m);
-                    t1[gi] = r;
-                    g.stat[(int64_t(s) * G + gi) * 2] = float(m);
-                    g.stat[(int64_t(s) * G + gi) * 2 + 1] = r;
-                } else {
-                    t0[gi] = float(a0);
-                    t1[gi] = float(a1);
-                }
-            }
-        }
-    }
-    __syncthreads();
-    if (MODE == 0) {
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            const float aa = t1[c / cpg] * g.gamma[c];
-            reinterpret_cast<float2*>(g.ab)[int64_t(s) * C + c] = make_float2(aa, g.beta[c] - t0[c / cpg] * aa);
-        }
-    } else {
-        const float invn = 1.0f / (float(g.P) * cpg);
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            const float mean = g.stat[(int64_t(s) * G + c / cpg) * 2];
-            const float rstd = g.stat[(int64_t(s) * G + c / cpg) * 2 + 1];
-            const float q = -rstd * rstd * t1[c / cpg] * invn;
-            reinterpret_cast<float4*>(g.coef)[int64_t(s) * C + c] =
-                make_float4(rstd * g.gamma[c], q, -rstd * t0[c / cpg] * invn - q * mean, 0.f);
-        }
+        for (int u = 0; u < 2; ++u)
+            if (p + u * lanes < p1) os[(p + u * lanes) * V] = apply(qx[u], qd[u], qa[u]);
     }
 }
 
@@ -459,22 +460,22 @@ __global__ void ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bf
 
 static size_t gn_smem(int C, int G) { return size_t(2 * C + 2 * G) * sizeof(float); }
 
-// Streaming geometry: threads = V * lanes (<= 256 where V allows), a block owns `chunk_pixels` pixels of one sample.
-// Apply modes want many small blocks (about 6 per SM: their latency chains overlap); sums modes pay 2C atomics per block,
-// so they use fewer, longer blocks.
+// Streaming geometry: threads = V * lanes (<= 256, or V itself up to 384 for the 2560- / 3072-channel concatenations), a block owns `chunk_pixels` pixels of one sample.  Apply modes want
+// several blocks per SM (their latency chains overlap) with at least four pixels per thread in flight; sums modes pay 2C
+// atomics per block, so they use fewer, longer blocks.
 static void gn_plan(GnArgs& g, int S, bool sums) {
     const int V = g.C / 8;
     g.lanes = std::max(1, 256 / V);
     const int sms = device_sm_count();
-    const int64_t want = std::max<int64_t>(1, ((sums ? 2 : 6) * sms + S - 1) / S);
-    const int64_t min_px = int64_t(g.lanes) * (sums ? 8 : 2);
+    const int64_t want = std::max<int64_t>(1, ((sums ? 2 : 4) * sms + S - 1) / S);
+    const int64_t min_px = int64_t(g.lanes) * (sums ? 8 : 4);
     const int64_t cp = std::max<int64_t>(min_px, (g.P + want - 1) / want);
     g.chunk_pixels = int(std::min<int64_t>(cp, g.P));
     g.chunks = int((g.P + g.chunk_pixels - 1) / g.chunk_pixels);
 }
 
 static int gn_check(const GnArgs& g) {
-    if (g.C % 8 || g.C % g.G || g.C / 8 > 512 || gn_smem(g.C, g.G) > 48 * 1024)
+    if (g.C % 8 || g.C % g.G || g.C / 8 > 384 || gn_smem(g.C, g.G) > 48 * 1024)
         return fail(-2, "groupnorm: C=%d G=%d unsupported", g.C, g.G);
     return 0;
 }
@@ -483,8 +484,7 @@ template <int MODE>
 static int gn_stream(GnArgs& g, int S, cudaStream_t st) {
     const bool sums = MODE == GN_BWD_SUMS || MODE == GN_FWD_SUMS;
     gn_plan(g, S, sums);
-    return int(launch_pdl(gn_stream_kernel<MODE>, dim3(S * g.chunks), dim3((g.C / 8) * g.lanes), sums ? size_t(2 * g.C) * sizeof(float) : size_t(0),
-                          st, g));
+    return int(launch_pdl(gn_stream_kernel<MODE>, dim3(S * g.chunks), dim3((g.C / 8) * g.lanes), gn_smem(g.C, g.G), st, g));
 }
 
 // Standalone per-sample channel sums of x [S][P][C] into stats (+=), row pitch ld channels.  Used by t2v_channel_stats and
@@ -507,7 +507,7 @@ extern "C" {
 
 int64_t t2v_groupnorm_workspace_bytes(int32_t S, int64_t P, int32_t C) {
     (void)P;
-    return int64_t(S) * C * 6 * sizeof(float);   // [S][C][2] sums + [S][C][4] backward coefficients
+    return int64_t(S) * C * 2 * sizeof(float);
 }
 
 int t2v_channel_stats(const void* x, float* stats, int32_t S, int64_t P, int32_t C, int64_t ld, void* stream_) {
@@ -534,8 +534,6 @@ int t2v_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void
         count_launch(1);
         g.stats0 = g.accum; g.stats1 = nullptr; g.C0 = C; g.ld0 = C; g.ld1 = 0; g.fps = 1;
     }
-    if (int rc = int(launch_pdl(gn_finalize_kernel<0>, dim3(S), dim3(256), gn_smem(C, G), st, g))) return launch_checked(rc, "groupnorm_fwd(finalise)");
-    count_launch(1);
     return launch_checked(gn_stream<GN_FWD_APPLY>(g, S, st), "groupnorm_fwd");
 }
 
@@ -554,10 +552,8 @@ int t2v_groupnorm_bwd(const void* dy, const void* x, const float* gamma, const f
     if (int r = gn_check(g)) return r;
     if (!workspace) return fail(-3, "groupnorm_bwd: needs a zeroed workspace");
     g.accum = static_cast<float*>(workspace);
-    g.coef = g.accum + int64_t(S) * C * 2;
     if (int rc = gn_stream<GN_BWD_SUMS>(g, S, st)) return launch_checked(rc, "groupnorm_bwd(sums)");
-    if (int rc = int(launch_pdl(gn_finalize_kernel<1>, dim3(S), dim3(256), gn_smem(C, G), st, g))) return launch_checked(rc, "groupnorm_bwd(finalise)");
-    count_launch(2);
+    count_launch(1);
     return launch_checked(gn_stream<GN_BWD_APPLY>(g, S, st), "groupnorm_bwd");
 }
 

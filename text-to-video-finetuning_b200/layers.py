@@ -127,7 +127,8 @@ class ResnetBlock2D(nn.Module):
         h = run_group_norm(self.norm2, h, True, N)
         if self.conv_shortcut is not None:
             x_skip = run_conv(self.conv_shortcut, x_skip, pads=(0, 0, 0, 0))
-        return run_conv(self.conv2, h, residual=x_skip, stats_rows=H * W)   # -> the GroupNorm of whatever comes next
+        # -> the per-clip GroupNorm of the TemporalConvLayer that follows every resnet of the UNet (frames_per_clip = 1: per frame)
+        return run_conv(self.conv2, h, residual=x_skip, stats_rows=frames_per_clip * H * W)
 
 
 class TemporalConvLayer(nn.Module):
@@ -164,7 +165,8 @@ class TemporalConvLayer(nn.Module):
                 h = ops.dropout(h, seq[2].p)
             h = h.view(B, num_frames, H * W, h.shape[-1])
             res = identity.view(B, num_frames, H * W, C) if i == 3 else None
-            h = run_conv(seq[-1], h, residual=res, pads=(1, 1, 0, 0), stats_rows=H * W)   # frame = (b, f): rows of one f-line
+            # the next stage normalises per clip; after conv4 (+ identity) a spatial layer follows, which normalises per frame
+            h = run_conv(seq[-1], h, residual=res, pads=(1, 1, 0, 0), stats_rows=(H * W) if i == 3 else num_frames * H * W)
             h = ops.view(h, N, H, W, -1)
         return h
 
@@ -337,7 +339,8 @@ class Transformer2DModel(nn.Module):
                                  attn.heads).view(B * Lq, -1)
 
         h = self.transformer_blocks[0](h, encoder_hidden_states, attend, attend_cross)
-        out = ops.view(run_linear(self.proj_out, h, residual=res.view(N * H * W, C), stats_rows=H * W), N, H, W, C)
+        # the TransformerTemporalModel that follows normalises per clip
+        out = ops.view(run_linear(self.proj_out, h, residual=res.view(N * H * W, C), stats_rows=num_frames * H * W), N, H, W, C)
         return SampleOutput(sample=out) if return_dict else (out,)
 
 

@@ -136,7 +136,7 @@ class UNet3DConditionModel(ModelMixin, ConfigMixin):
         emb = self.time_embedding(self.time_proj(timesteps))
         sc = StepContext(num_frames, ops.silu(emb), text)
 
-        h = run_conv(self.conv_in, x, cin_pad=8 - cfg.in_channels, stats_rows=H * W)
+        h = run_conv(self.conv_in, x, cin_pad=8 - cfg.in_channels, stats_rows=num_frames * H * W)   # -> transformer_in (per clip)
         if num_frames > 1:
             h = transformer_g_c(self.transformer_in, h, num_frames, self.gradient_checkpointing)
 

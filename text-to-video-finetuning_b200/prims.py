@@ -221,7 +221,7 @@ def groupnorm_bwd(dy, x, gamma, stat, ab, G, silu, add=None, dgamma=None, dbeta=
     _chk_bf16(dy, x, add)
     S, P, C = x.shape
     dx = torch.empty_like(x)
-    ws = zeros_f32((S, C, 6), x.device)   # [S][C][2] sums (red.add targets: zero on entry) + [S][C][4] coefficients
+    ws = zeros_f32((S, C, 2), x.device)   # per-channel sums (red.add targets: zero on entry)
     native.check(native.lib().t2v_groupnorm_bwd(_p(dy), _p(x), _p(gamma), _p(stat), _p(ab), _p(add), _p(dx), _p(dgamma), _p(dbeta),
                                                 _p(ws), S, P, C, G, int(silu), _stream()))
     return dx
