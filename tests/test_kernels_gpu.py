@@ -272,6 +272,8 @@ def test_attention_composite(Nb, Lq, Lk, heads, D):
     ((16, 4, 4, 128), 256, (3, 3), 1, (1, 1, 1, 1), 16 * 16, True, "per-clip statistics at the 4x4 level (one sample)"),
     ((16, 32, 32, 8), 320, (3, 3), 1, (1, 1, 1, 1), 16 * 1024, False, "conv_in -> transformer_in (per clip, 8 input channels)"),
     ((1, 1, 16384, 320), 320, (1, 1), 1, (0, 0, 0, 0), 16384, True, "linear, one sample over all rows"),
+    ((1, 16, 1024, 64), 128, (3, 1), 1, (1, 1, 0, 0), 4 * 1024, True, "temporal conv, slots of 4 frames (clip_stats_rows)"),
+    ((2, 8, 64, 64), 128, (3, 1), 1, (1, 1, 0, 0), 8 * 64, False, "temporal conv, one slot per clip"),
 ])
 def test_conv_epilogue_statistics(case):
     """T2VEpilogue.stats: the per-(frame, channel) sums a GEMM epilogue (or its split-K finishing pass, or the fallback

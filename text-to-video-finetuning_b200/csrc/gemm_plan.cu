@@ -236,9 +236,15 @@ bool plan_epilogue_stats(GemmParams& p, const T2VEpilogue* e, int Wo, int Ho, in
             const int64_t m = sg / fp;                           // the run covers m consecutive images of the tile
             return k % m == 0 && p.bn % m == 0;
         });
-    } else if (pf == Wo) {                // a sample is one h-line (temporal layout [B][F][HW]: frame = (n, h))
-        ch = 1; cn = Ho;
-        seg = pick_seg([&](int sg) { return p.bw % sg == 0; });
+    } else if (pf % Wo == 0 && Ho % (pf / Wo) == 0) {   // a sample is k h-lines (temporal layout [B][F][HW]: h = frame index)
+        const int64_t k = pf / Wo;
+        ch = 1; cn = Ho; div = int(k);
+        seg = pick_seg([&](int sg) {
+            if (p.bw % sg == 0) return true;                     // the run stays inside one h-line
+            if (sg % p.bw) return false;
+            const int64_t m = sg / p.bw;                         // the run covers m consecutive h-lines of the tile
+            return k % m == 0 && p.bh % m == 0;
+        });
     } else if (Ho == 1 && N == 1 && Wo % pf == 0) {   // token matrix: sample = row / pf
         cw = 1; div = int(pf);
         seg = (p.bh == 1 && p.bn == 1) ? pick_seg([&](int sg) { return pf % sg == 0; }) : 0;

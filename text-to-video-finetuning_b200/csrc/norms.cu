@@ -24,7 +24,13 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
     q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]); q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
     return q;
 }
-__device__ __forceinline__ float sigmoidf_(float z) { return 1.0f / (1.0f + __expf(-z)); }
+// sigmoid(z) = 0.5 tanh(z / 2) + 0.5 on the hardware tanh: one MUFU op instead of two (ex2 + rcp); absolute error < 3e-4,
+// an order of magnitude below the bf16 rounding of the values it feeds
+__device__ __forceinline__ float sigmoidf_(float z) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
+    return fmaf(0.5f, t, 0.5f);
+}
 
 // ------------------------------------------------------------------------------------------------ GroupNorm
 // Streaming kernels with many small blocks (<= 256 threads, several resident per SM, so the per-block latency chain
@@ -61,7 +67,7 @@ struct GnArgs {
 enum { GN_FWD_APPLY = 0, GN_BWD_SUMS = 1, GN_BWD_APPLY = 2, GN_FWD_SUMS = 3 };
 
 template <int MODE>
-__global__ void __launch_bounds__(384) gn_stream_kernel(const GnArgs g) {
+__global__ void __launch_bounds__(384, 2) gn_stream_kernel(const GnArgs g) {
     pdl_sync();
     extern __shared__ float sh[];  // [2][C] per-channel sums, then [2][G] group terms
     constexpr bool kSums = MODE == GN_BWD_SUMS || MODE == GN_FWD_SUMS;
@@ -71,10 +77,13 @@ __global__ void __launch_bounds__(384) gn_stream_kernel(const GnArgs g) {
     const int V = C >> 3;
     const int lanes = g.lanes;
     const int cv = threadIdx.x % V, pl = threadIdx.x / V;
+    // block-local 32-bit addressing: the chunk starts at pixel p0 of sample s; this thread walks pixels pl, pl + lanes, ...
     const int64_t p0 = int64_t(chunk) * g.chunk_pixels;
-    const int64_t p1 = min(g.P, p0 + g.chunk_pixels);
-    const uint4* xs = reinterpret_cast<const uint4*>(g.x + int64_t(s) * g.P * C) + cv;
-    const uint4* ds = kBwd ? reinterpret_cast<const uint4*>(g.dy + int64_t(s) * g.P * C) + cv : nullptr;
+    const int np = int(min(g.P, p0 + g.chunk_pixels) - p0);          // pixels of this chunk
+    const int64_t base = (int64_t(s) * g.P + p0) * V + cv;            // in 16-byte vectors
+    const uint4* xs = reinterpret_cast<const uint4*>(g.x) + base;
+    const uint4* ds = kBwd ? reinterpret_cast<const uint4*>(g.dy) + base : nullptr;
+    const int stepv = lanes * V;                                      // vector stride between a thread's consecutive pixels
     float* cs = sh;              // [2][C]
     float* t0 = sh + 2 * C;      // [G]  fwd: group mean   bwd: sum_c gamma * sum dz
     float* t1 = t0 + G;          // [G]  fwd: group rstd   bwd: sum_c gamma * sum dz*xhat
@@ -92,7 +101,8 @@ __global__ void __launch_bounds__(384) gn_stream_kernel(const GnArgs g) {
                 const float2* src = reinterpret_cast<const float2*>(first ? g.stats0 : g.stats1) + (first ? c : c - g.C0);
                 const int64_t ld = first ? g.ld0 : g.ld1;
                 float a0 = 0.f, a1 = 0.f;
-                for (int f = 0; f < g.fps; ++f) {   // fps == 1 when the producer summed at this norm's granularity
+#pragma unroll 4
+                for (int f = 0; f < g.fps; ++f) {   // a few slots per sample (layers.clip_stats_rows): independent loads
                     const float2 v = __ldcg(src + (int64_t(s) * g.fps + f) * ld);
                     a0 += v.x;
                     a1 += v.y;
@@ -164,7 +174,7 @@ __global__ void __launch_bounds__(384) gn_stream_kernel(const GnArgs g) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) reinterpret_cast<float2*>(g.ab)[int64_t(s) * C + cv * 8 + j] = make_float2(a[j], b[j]);
         }
-        uint4* os = reinterpret_cast<uint4*>(g.out + int64_t(s) * g.P * C) + cv;
+        uint4* os = reinterpret_cast<uint4*>(g.out) + base;
         auto apply = [&](const uint4& qx) {
             float v[8];
             unpack8(qx, v);
@@ -176,14 +186,14 @@ __global__ void __launch_bounds__(384) gn_stream_kernel(const GnArgs g) {
             }
             return pack8(v);
         };
-        for (int64_t p = p0 + pl; p < p1; p += 4 * lanes) {   // four pixels in flight, the tail is predicated (not serialised)
+        for (int p = pl, off = pl * V; p < np; p += 4 * lanes, off += 4 * stepv) {   // four pixels in flight, predicated tail
             uint4 qx[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (p + u * lanes < p1) qx[u] = __ldg(xs + (p + u * lanes) * V);
+                if (p + u * lanes < np) qx[u] = __ldg(xs + off + u * stepv);
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (p + u * lanes < p1) os[(p + u * lanes) * V] = apply(qx[u]);
+                if (p + u * lanes < np) os[off + u * stepv] = apply(qx[u]);
         }
         return;
     }
@@ -236,18 +246,18 @@ __global__ void __launch_bounds__(384) gn_stream_kernel(const GnArgs g) {
             }
         };
         constexpr int U = MODE == GN_FWD_SUMS ? 4 : 2;
-        for (int64_t p = p0 + pl; p < p1; p += U * lanes) {
+        for (int p = pl, off = pl * V; p < np; p += U * lanes, off += U * stepv) {
             uint4 qx[U], qd[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (p + u * lanes < p1) {
-                    qx[u] = __ldg(xs + (p + u * lanes) * V);
-                    if (kBwd) qd[u] = __ldg(ds + (p + u * lanes) * V);
+                if (p + u * lanes < np) {
+                    qx[u] = __ldg(xs + off + u * stepv);
+                    if (kBwd) qd[u] = __ldg(ds + off + u * stepv);
                 }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (p + u * lanes < p1) accumulate(qx[u], qd[u]);
+                if (p + u * lanes < np) accumulate(qx[u], qd[u]);
         }
         if (lanes == 1) {   // one pixel lane per channel vector: no contention, plain stores
 #pragma unroll
@@ -279,8 +289,8 @@ __global__ void __launch_bounds__(384) gn_stream_kernel(const GnArgs g) {
         qc[j] = q;
         rc[j] = -rstd[j] * t0[c / cpg] * invn - q * mean[j];
     }
-    uint4* os = reinterpret_cast<uint4*>(g.out + int64_t(s) * g.P * C) + cv;
-    const uint4* as = g.add ? reinterpret_cast<const uint4*>(g.add + int64_t(s) * g.P * C) + cv : nullptr;
+    uint4* os = reinterpret_cast<uint4*>(g.out) + base;
+    const uint4* as = g.add ? reinterpret_cast<const uint4*>(g.add) + base : nullptr;
     auto apply = [&](const uint4& qx, const uint4& qd, const uint4& qa) {
         float v[8], d[8], r[8];
         unpack8(qx, v);
@@ -299,19 +309,19 @@ __global__ void __launch_bounds__(384) gn_stream_kernel(const GnArgs g) {
         return pack8(v);
     };
     const uint4 zero = make_uint4(0, 0, 0, 0);
-    for (int64_t p = p0 + pl; p < p1; p += 2 * lanes) {
+    for (int p = pl, off = pl * V; p < np; p += 2 * lanes, off += 2 * stepv) {
         uint4 qx[2], qd[2], qa[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            if (p + u * lanes < p1) {
-                qx[u] = __ldg(xs + (p + u * lanes) * V);
-                qd[u] = __ldg(ds + (p + u * lanes) * V);
-                qa[u] = as ? __ldg(as + (p + u * lanes) * V) : zero;
+            if (p + u * lanes < np) {
+                qx[u] = __ldg(xs + off + u * stepv);
+                qd[u] = __ldg(ds + off + u * stepv);
+                qa[u] = as ? __ldg(as + off + u * stepv) : zero;
             }
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u)
-            if (p + u * lanes < p1) os[(p + u * lanes) * V] = apply(qx[u], qd[u], qa[u]);
+            if (p + u * lanes < np) os[off + u * stepv] = apply(qx[u], qd[u], qa[u]);
     }
 }
 

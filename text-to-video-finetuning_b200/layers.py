@@ -56,6 +56,17 @@ def run_conv(m, x, rowbias=None, residual=None, stride=1, pads=(1, 1, 1, 1), rb_
     return ops.conv(x, m.weight, m.bias, rowbias, residual, stride, pads, rb_div, False, cin_pad, cout_pad, stats_rows=stats_rows)
 
 
+def clip_stats_rows(num_frames, hw):
+    """Rows per statistics slot for a producer whose consumer normalises per CLIP.  One slot per clip would make every tile
+    of a 16,384-row output red.add into the same C addresses (512-way same-address contention in L2, measured +7 us per
+    GEMM); slots of about 4,096 rows (a whole number of frames, dividing the clip) keep the contention near that of the
+    per-frame case, and the consumer adds the few slots of a clip while it finalises."""
+    f = max(1, min(num_frames, 4096 // max(1, hw)))
+    while num_frames % f:
+        f -= 1
+    return f * hw
+
+
 def run_group_norm(m, x, silu, samples):
     return ops.group_norm(x, m.weight, m.bias, m.num_groups, m.eps, silu, samples)
 
@@ -128,7 +139,7 @@ class ResnetBlock2D(nn.Module):
         if self.conv_shortcut is not None:
             x_skip = run_conv(self.conv_shortcut, x_skip, pads=(0, 0, 0, 0))
         # -> the per-clip GroupNorm of the TemporalConvLayer that follows every resnet of the UNet (frames_per_clip = 1: per frame)
-        return run_conv(self.conv2, h, residual=x_skip, stats_rows=frames_per_clip * H * W)
+        return run_conv(self.conv2, h, residual=x_skip, stats_rows=clip_stats_rows(frames_per_clip, H * W))
 
 
 class TemporalConvLayer(nn.Module):
@@ -166,7 +177,7 @@ class TemporalConvLayer(nn.Module):
             h = h.view(B, num_frames, H * W, h.shape[-1])
             res = identity.view(B, num_frames, H * W, C) if i == 3 else None
             # the next stage normalises per clip; after conv4 (+ identity) a spatial layer follows, which normalises per frame
-            h = run_conv(seq[-1], h, residual=res, pads=(1, 1, 0, 0), stats_rows=(H * W) if i == 3 else num_frames * H * W)
+            h = run_conv(seq[-1], h, residual=res, pads=(1, 1, 0, 0), stats_rows=(H * W) if i == 3 else clip_stats_rows(num_frames, H * W))
             h = ops.view(h, N, H, W, -1)
         return h
 
@@ -340,7 +351,7 @@ class Transformer2DModel(nn.Module):
 
         h = self.transformer_blocks[0](h, encoder_hidden_states, attend, attend_cross)
         # the TransformerTemporalModel that follows normalises per clip
-        out = ops.view(run_linear(self.proj_out, h, residual=res.view(N * H * W, C), stats_rows=num_frames * H * W), N, H, W, C)
+        out = ops.view(run_linear(self.proj_out, h, residual=res.view(N * H * W, C), stats_rows=clip_stats_rows(num_frames, H * W)), N, H, W, C)
         return SampleOutput(sample=out) if return_dict else (out,)
 
 

@@ -14,7 +14,8 @@ import torch
 import torch.nn as nn
 
 from .. import ops, prims
-from ..layers import TimestepEmbedding, Timesteps, TransformerTemporalModel, _channels_last_, run_conv, run_group_norm
+from ..layers import (TimestepEmbedding, Timesteps, TransformerTemporalModel, _channels_last_, clip_stats_rows, run_conv,
+                      run_group_norm)
 from ..modeling_utils import ConfigMixin, ModelMixin, register_to_config
 from .unet_3d_blocks import (CrossAttnDownBlock3D, CrossAttnUpBlock3D, DownBlock3D, StepContext, UNetMidBlock3DCrossAttn,
                              UpBlock3D, get_down_block, get_up_block, transformer_g_c)
@@ -136,7 +137,7 @@ class UNet3DConditionModel(ModelMixin, ConfigMixin):
         emb = self.time_embedding(self.time_proj(timesteps))
         sc = StepContext(num_frames, ops.silu(emb), text)
 
-        h = run_conv(self.conv_in, x, cin_pad=8 - cfg.in_channels, stats_rows=num_frames * H * W)   # -> transformer_in (per clip)
+        h = run_conv(self.conv_in, x, cin_pad=8 - cfg.in_channels, stats_rows=clip_stats_rows(num_frames, H * W))   # -> transformer_in (per clip)
         if num_frames > 1:
             h = transformer_g_c(self.transformer_in, h, num_frames, self.gradient_checkpointing)
 
