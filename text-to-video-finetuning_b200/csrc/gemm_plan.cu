@@ -257,45 +257,61 @@ bool plan_epilogue_stats(GemmParams& p, const T2VEpilogue* e, int Wo, int Ho, in
     return true;
 }
 
-// Finishing pass of a split-K problem that also produces the GroupNorm statistics of its output: a block owns `rpb`
-// consecutive rows of ONE frame and all columns; a thread owns column quads and walks the rows.
-__global__ void splitk_finish_stats_kernel(const float* __restrict__ acc, const float* __restrict__ bias, const float* __restrict__ rowbias,
-                                           const __nv_bfloat16* __restrict__ residual, void* __restrict__ out, int64_t rows, int C,
-                                           int64_t rows_per_sample, int rb_div, int64_t rb_ld, float alpha, int out_fp32,
-                                           float* __restrict__ stats, int64_t st_ld, int st_rows, int rpb) {
+// Finishing pass of a split-K problem that also produces the GroupNorm statistics of its output: a block owns RPB
+// consecutive rows of ONE statistics sample and 256 column quads; a thread loads its quad of all RPB rows up front (independent
+// loads: one memory round trip), finishes them, and adds the column sums with two red.add.v4.
+template <int RPB>
+__global__ void __launch_bounds__(256) splitk_finish_stats_kernel(const float* __restrict__ acc, const float* __restrict__ bias,
+                                                                  const float* __restrict__ rowbias, const __nv_bfloat16* __restrict__ residual,
+                                                                  void* __restrict__ out, int64_t rows, int C, int64_t rows_per_sample, int rb_div,
+                                                                  int64_t rb_ld, float alpha, int out_fp32, float* __restrict__ stats,
+                                                                  int64_t st_ld, int st_rows) {
     pdl_sync();
-    const int64_t r0 = int64_t(blockIdx.x) * rpb;
-    const int64_t r1 = min(rows, r0 + rpb);
-    float* sp = stats + (r0 / st_rows) * st_ld * 2;
-    for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + c));
-        float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int64_t r = r0; r < r1; ++r) {
-            float4 v = __ldcg(reinterpret_cast<const float4*>(acc + r * C + c));
-            v.x = v.x * alpha + b4.x; v.y = v.y * alpha + b4.y; v.z = v.z * alpha + b4.z; v.w = v.w * alpha + b4.w;
-            if (rowbias) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(rowbias + (r / rows_per_sample / rb_div) * rb_ld + c));
-                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-            }
-            if (residual) {
-                const uint2 w = __ldg(reinterpret_cast<const uint2*>(residual + r * C + c));
-                v.x += bf16_lo(w.x); v.y += bf16_hi(w.x); v.z += bf16_lo(w.y); v.w += bf16_hi(w.y);
-            }
-            if (out_fp32) {
-                reinterpret_cast<float4*>(static_cast<float*>(out) + r * C)[c >> 2] = v;
-            } else {
-                uint2 w;
-                w.x = pack_bf16(v.x, v.y);
-                w.y = pack_bf16(v.z, v.w);
-                reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out) + r * C)[c >> 2] = w;
-            }
-            s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-            q[0] += v.x * v.x; q[1] += v.y * v.y; q[2] += v.z * v.z; q[3] += v.w * v.w;
+    const int64_t r0 = int64_t(blockIdx.x) * RPB;
+    const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+    if (c >= C) return;
+    float4 v[RPB];
+    uint2 w[RPB];
+#pragma unroll
+    for (int i = 0; i < RPB; ++i) {
+        const int64_t r = r0 + i;
+        if (r < rows) {
+            v[i] = __ldcg(reinterpret_cast<const float4*>(acc + r * C + c));
+            if (residual) w[i] = __ldg(reinterpret_cast<const uint2*>(residual + r * C + c));
         }
-        red_add_f32x4(sp + 2 * c, s[0], q[0], s[1], q[1]);
-        red_add_f32x4(sp + 2 * c + 4, s[2], q[2], s[3], q[3]);
     }
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + c));
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < RPB; ++i) {
+        const int64_t r = r0 + i;
+        if (r >= rows) break;
+        float4 y = v[i];
+        y.x = y.x * alpha + b4.x; y.y = y.y * alpha + b4.y; y.z = y.z * alpha + b4.z; y.w = y.w * alpha + b4.w;
+        if (rowbias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(rowbias + (r / rows_per_sample / rb_div) * rb_ld + c));
+            y.x += b.x; y.y += b.y; y.z += b.z; y.w += b.w;
+        }
+        if (residual) {
+            y.x += bf16_lo(w[i].x); y.y += bf16_hi(w[i].x); y.z += bf16_lo(w[i].y); y.w += bf16_hi(w[i].y);
+        }
+        if (out_fp32) {
+            reinterpret_cast<float4*>(static_cast<float*>(out) + r * C)[c >> 2] = y;
+        } else {
+            uint2 o;
+            o.x = pack_bf16(y.x, y.y);
+            o.y = pack_bf16(y.z, y.w);
+            reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out) + r * C)[c >> 2] = o;
+            // the statistics describe what the consumer reads: the rounded values
+            y.x = bf16_lo(o.x); y.y = bf16_hi(o.x); y.z = bf16_lo(o.y); y.w = bf16_hi(o.y);
+        }
+        s[0] += y.x; s[1] += y.y; s[2] += y.z; s[3] += y.w;
+        q[0] += y.x * y.x; q[1] += y.y * y.y; q[2] += y.z * y.z; q[3] += y.w * y.w;
+    }
+    float* sp = stats + ((r0 / st_rows) * st_ld + c) * 2;
+    red_add_f32x4(sp, s[0], q[0], s[1], q[1]);
+    red_add_f32x4(sp + 4, s[2], q[2], s[3], q[3]);
 }
 
 __global__ void splitk_finish_kernel(const float* __restrict__ acc, const float* __restrict__ bias, const float* __restrict__ rowbias,
@@ -346,14 +362,16 @@ int launch_split(GemmParams& p, bool a_mn, bool b_mn, const T2VEpilogue& e, void
     set_vec_flag(p);
     if (int r = launch_checked(launch_gemm(p, a_mn, b_mn, st), what)) return r;
     if (e.stats && e.stats_rows > 0 && e.stats_ld % 2 == 0 && (reinterpret_cast<uintptr_t>(e.stats) & 15u) == 0) {
-        int rpb = 0;   // rows per block: a divisor of the frame's rows, so a block never straddles two frames
-        for (int cand : {16, 8, 4, 2, 1})
-            if (e.stats_rows % cand == 0) { rpb = cand; break; }
-        const int64_t blocks = (rows + rpb - 1) / rpb;
-        const int rc = int(launch_pdl(splitk_finish_stats_kernel, dim3(unsigned(blocks)), dim3(std::min(256, std::max(32, C / 4))), 0, st,
-                                      static_cast<const float*>(e.workspace), e.bias, e.rowbias, static_cast<const __nv_bfloat16*>(e.residual),
-                                      out, rows, C, rows_per_sample, e.rowbias_div > 0 ? e.rowbias_div : 1, int64_t(C), e.alpha, e.out_fp32,
-                                      e.stats, e.stats_ld, e.stats_rows, rpb));
+        // rows per block: a divisor of the sample's rows, so a block never straddles two samples
+        const int rpb = e.stats_rows % 4 == 0 ? 4 : (e.stats_rows % 2 == 0 ? 2 : 1);
+        const dim3 grid(unsigned((rows + rpb - 1) / rpb), unsigned((C / 4 + 255) / 256));
+        const dim3 block(unsigned(std::min(256, (C / 4 + 31) / 32 * 32)));
+        auto go = [&](auto kern) {
+            return int(launch_pdl(kern, grid, block, 0, st, static_cast<const float*>(e.workspace), e.bias, e.rowbias,
+                                  static_cast<const __nv_bfloat16*>(e.residual), out, rows, C, rows_per_sample,
+                                  e.rowbias_div > 0 ? e.rowbias_div : 1, int64_t(C), e.alpha, e.out_fp32, e.stats, e.stats_ld, e.stats_rows));
+        };
+        const int rc = rpb == 4 ? go(splitk_finish_stats_kernel<4>) : (rpb == 2 ? go(splitk_finish_stats_kernel<2>) : go(splitk_finish_stats_kernel<1>));
         return launch_checked(rc, what);
     }
     const int64_t vec = rows * (C / 4);
