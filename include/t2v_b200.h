@@ -188,6 +188,10 @@ int t2v_add_bf16(const void* a, const void* b, const void* c, void* out, int64_t
 int t2v_scale_bf16(const void* a, void* out, int64_t n, float alpha, void* stream);
 int t2v_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream);
 int t2v_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* Gradient compression around the data-parallel all-reduce (the reference reduces through accelerate/DDP, train.py:661,861):
+ * dst (bf16) = alpha * src (fp32), alpha = 1 / world so that a SUM all-reduce averages; and the widening inverse.          */
+int t2v_scale_cast_f32_bf16(const float* src, void* dst, int64_t n, float alpha, void* stream);
+int t2v_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream);
 
 /* nn.Dropout fused with the LoRA branch / TemporalConvLayer stage: out = base + scale * x * mask / (1 - p), mask drawn
  * from a stateless counter-based generator keyed by (seed, element index); calling it again with the same seed on dy
@@ -236,11 +240,13 @@ int t2v_attn_small_bwd(const void* q, const void* k, const void* v, const void* 
  *                       eps, weight_decay) writes hp[s] = (.., bias_c1, sqrt(bias_c2), clip factor); the clip factor is
  *                       min(1, max_norm / (sqrt(sq[0]) + 1e-6)) (1 when max_norm <= 0); sq[1] = norm, sq[0] = 0
  *   t2v_adamw_chunks    updates p, m, v from g * clip, writes the bf16 compute copy of p for offsets < n_shadow (shadow may be
- *                       NULL) and zeroes g when zero_grad != 0.  hp points at ONE 8-float row.                           */
-int t2v_sqnorm_chunks(const float* g, const int64_t* chunks, int32_t n_chunks, double* out, void* stream);
+ *                       NULL) and zeroes g when zero_grad != 0.  hp points at ONE 8-float row.
+ * g_bf16 (sqnorm, adamw_chunks; may be NULL): flat bf16 buffer with the same offsets as g - when given, the gradient VALUES are
+ * read from it (the all-reduced, averaged gradient of a data-parallel step) and the fp32 buffer g is only zeroed.        */
+int t2v_sqnorm_chunks(const float* g, const void* g_bf16, const int64_t* chunks, int32_t n_chunks, double* out, void* stream);
 int t2v_adamw_prepare(const float* hp_in, float* hp, int32_t n_sets, int64_t* state, double* sq, float max_norm, void* stream);
-int t2v_adamw_chunks(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_t n_shadow, const int64_t* chunks, int32_t n_chunks,
-                     const float* hp, int32_t zero_grad, void* stream);
+int t2v_adamw_chunks(float* p, float* g, const void* g_bf16, float* m, float* v, void* shadow_bf16, int64_t n_shadow, const int64_t* chunks,
+                     int32_t n_chunks, const float* hp, int32_t zero_grad, void* stream);
 
 #ifdef __cplusplus
 }

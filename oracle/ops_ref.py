@@ -254,9 +254,18 @@ def counter_add(counter, value=1):
 
 
 @torch.no_grad()
-def sqnorm_chunks(g, chunks, out):
+def sqnorm_chunks(g, chunks, out, g_bf16=None):
+    src = g if g_bf16 is None else g_bf16
     for off, n in chunks.tolist():
-        out[0] += g[off:off + n].double().pow(2).sum()
+        out[0] += src[off:off + n].double().pow(2).sum()
+
+
+def scale_cast_f32_bf16(src, dst, alpha):
+    dst.copy_((src * alpha).to(dst.dtype))
+
+
+def cast_bf16_f32(src, dst):
+    dst.copy_(src.float())
 
 
 @torch.no_grad()
@@ -277,12 +286,12 @@ def adamw_prepare(hp_in, hp, state, sq, max_norm):
 
 
 @torch.no_grad()
-def adamw_chunks(p, g, m, v, shadow, n_shadow, chunks, hp_row, zero_grad=True):
+def adamw_chunks(p, g, m, v, shadow, n_shadow, chunks, hp_row, zero_grad=True, g_bf16=None):
     """torch.optim.AdamW's single-tensor update on the chunk table (same arithmetic order as the kernel)."""
     lr, b1, b2, eps, wd, bc1, bc2s, gscale = (float(x) for x in hp_row.tolist())
     for off, n in chunks.tolist():
         sl = slice(off, off + n)
-        gs = g[sl] * gscale
+        gs = (g[sl] if g_bf16 is None else g_bf16[sl].float()) * gscale
         p[sl].mul_(1.0 - lr * wd)
         m[sl].mul_(b1).add_(gs, alpha=1.0 - b1)
         v[sl].mul_(b2).addcmul_(gs, gs, value=1.0 - b2)

@@ -21,7 +21,8 @@ def _inputs():
     return lat, noise, t, ehs
 
 
-def _worker(rank, world, port, out_path):
+def _worker(rank, world, port, out_path, compress="0"):
+    os.environ["T2V_GRAD_COMPRESS"] = compress
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -43,20 +44,28 @@ def _worker(rank, world, port, out_path):
         loss = st(lat[sl], noise[sl], t[sl], ehs[sl])
     if rank == 0:
         torch.save({"loss": loss, "grads": {n: p.grad.clone() for n, p in m.named_parameters()}, "arena_total": st.arena.total,
-                    "overlapped": st.buckets.last_overlapped, "blocks": len(st.buckets.ranges)}, out_path)
+                    "overlapped": st.buckets.last_overlapped, "blocks": len(st.buckets.ranges), "wire": st.buckets.bytes_on_wire,
+                    "compress": st.buckets.compress}, out_path)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_rank_allreduce_matches_two_clip_oracle(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("compress", ["0", "1"])
+def test_two_rank_allreduce_matches_two_clip_oracle(tmp_path, compress):
+    """compress = 1: gradients cross the wire as bf16 (scaled by 1 / world before rounding), half the bytes."""
     from helpers import rel_l2, seeded_state_dict
     from oracle import leaves as L
     from oracle import unet3d_ref as R
     from t2v_b200.models.unet_3d_condition import UNet3DConditionModel
     out = str(tmp_path / "rank0.pt")
     port = 29500 + os.getpid() % 2000
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, out, compress), nprocs=2, join=True)
     got = torch.load(out, weights_only=False)
+    assert got["compress"] == (compress == "1")
+    assert got["wire"] == got["arena_total"] * (2 if compress == "1" else 4), (got["wire"], got["arena_total"])
     # every top-level block's gradient all-reduce was issued from inside the backward pass (4 down + mid + 4 up)
     assert got["blocks"] == 9 and got["overlapped"] == 9, (got["blocks"], got["overlapped"])
     with torch.device("meta"):

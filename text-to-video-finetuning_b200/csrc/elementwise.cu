@@ -233,6 +233,30 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
     if (blockIdx.x == 0 && threadIdx.x < (n & 7)) dst[(nv << 3) + threadIdx.x] = __float2bfloat16_rn(src[(nv << 3) + threadIdx.x]);
 }
 
+// Gradient compression for the data-parallel all-reduce: dst (bf16) = alpha * src (fp32); and its inverse (widening).
+__global__ void scale_cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n, float alpha) {
+    pdl_sync();
+    const int64_t nv = n >> 3;
+    GRID_STRIDE(i, nv) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+        const float v[8] = {a.x * alpha, a.y * alpha, a.z * alpha, a.w * alpha, b.x * alpha, b.y * alpha, b.z * alpha, b.w * alpha};
+        reinterpret_cast<uint4*>(dst)[i] = pack8e(v);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 7)) dst[(nv << 3) + threadIdx.x] = __float2bfloat16_rn(alpha * src[(nv << 3) + threadIdx.x]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int64_t n) {
+    pdl_sync();
+    const int64_t nv = n >> 3;
+    GRID_STRIDE(i, nv) {
+        float v[8];
+        unpack8e(__ldg(reinterpret_cast<const uint4*>(src) + i), v);
+        reinterpret_cast<float4*>(dst)[2 * i] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(dst)[2 * i + 1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 7)) dst[(nv << 3) + threadIdx.x] = __bfloat162float(src[(nv << 3) + threadIdx.x]);
+}
+
 // ------------------------------------------------------------------------------------------------ resampling / concat
 // nearest-neighbour resize [N][H][W][C] -> [N][Ho][Wo][C]  (src = floor(dst * in / out), F.interpolate 'nearest')
 __global__ void upsample_nearest_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
@@ -517,6 +541,16 @@ int t2v_scale_bf16(const void* a, void* out, int64_t n, float alpha, void* strea
 int t2v_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream) {
     launch_pdl(add_f32_kernel, dim3(ew_grid(n)), dim3(256), size_t(0), ST, a, b, out, n);
     return launch_checked(int(cudaGetLastError()), "add_f32");
+}
+int t2v_scale_cast_f32_bf16(const float* src, void* dst, int64_t n, float alpha, void* stream) {
+    if ((reinterpret_cast<uintptr_t>(src) & 15u) || (reinterpret_cast<uintptr_t>(dst) & 15u)) return fail(-2, "scale_cast_f32_bf16: 16-byte alignment");
+    launch_pdl(scale_cast_f32_bf16_kernel, dim3(ew_grid(std::max<int64_t>(n / 8, 1))), dim3(256), size_t(0), ST, src, BFW(dst), n, alpha);
+    return launch_checked(int(cudaGetLastError()), "scale_cast_f32_bf16");
+}
+int t2v_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream) {
+    if ((reinterpret_cast<uintptr_t>(src) & 15u) || (reinterpret_cast<uintptr_t>(dst) & 15u)) return fail(-2, "cast_bf16_f32: 16-byte alignment");
+    launch_pdl(cast_bf16_f32_kernel, dim3(ew_grid(std::max<int64_t>(n / 8, 1))), dim3(256), size_t(0), ST, BF(src), dst, n);
+    return launch_checked(int(cudaGetLastError()), "cast_bf16_f32");
 }
 int t2v_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
     launch_pdl(cast_f32_bf16_kernel, dim3(ew_grid(std::max<int64_t>(n / 8, 1))), dim3(256), size_t(0), ST, src, BFW(dst), n);

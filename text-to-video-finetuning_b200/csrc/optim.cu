@@ -42,10 +42,12 @@ __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v,
     p -= (a.lr / a.bias_c1) * (m / denom);
 }
 
+// g16 != NULL: the gradient comes from the bf16 communication buffer (the all-reduced, averaged gradient of a data-parallel
+// step); the fp32 accumulation buffer g is then only zeroed.
 __global__ void __launch_bounds__(256) adamw_chunks_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                                            float* __restrict__ v, __nv_bfloat16* __restrict__ shadow, int64_t n_shadow,
                                                            const int64_t* __restrict__ chunks, int n_chunks, const float* __restrict__ hp,
-                                                           int zero_grad) {
+                                                           int zero_grad, const __nv_bfloat16* __restrict__ g16) {
     pdl_sync();
     AdamWArgs a;
     a.lr = hp[0]; a.beta1 = hp[1]; a.beta2 = hp[2]; a.eps = hp[3]; a.weight_decay = hp[4];
@@ -58,10 +60,17 @@ __global__ void __launch_bounds__(256) adamw_chunks_kernel(float* __restrict__ p
         float4* m4 = reinterpret_cast<float4*>(m + off);
         float4* v4 = reinterpret_cast<float4*>(v + off);
         uint2* s2 = reinterpret_cast<uint2*>(shadow + off);
+        const uint2* h2 = reinterpret_cast<const uint2*>(g16 + off);
         const int nv = int(len >> 2);
         for (int i = threadIdx.x; i < nv; i += blockDim.x) {
             float4 pp = p4[i];
-            const float4 gg = g4[i];
+            float4 gg;
+            if (g16) {
+                const uint2 h = __ldg(h2 + i);
+                gg = make_float4(bf16_lo(h.x), bf16_hi(h.x), bf16_lo(h.y), bf16_hi(h.y));
+            } else {
+                gg = g4[i];
+            }
             float4 mm = m4[i];
             float4 vv = v4[i];
             adamw_one(pp.x, gg.x, mm.x, vv.x, a);
@@ -83,16 +92,23 @@ __global__ void __launch_bounds__(256) adamw_chunks_kernel(float* __restrict__ p
 }
 
 __global__ void __launch_bounds__(256) sqnorm_chunks_kernel(const float* __restrict__ g, const int64_t* __restrict__ chunks, int n_chunks,
-                                                            double* __restrict__ out) {
+                                                            double* __restrict__ out, const __nv_bfloat16* __restrict__ g16) {
     pdl_sync();
     double acc = 0.0;
     for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
         const int64_t off = chunks[2 * c], len = chunks[2 * c + 1];
         const float4* g4 = reinterpret_cast<const float4*>(g + off);
+        const uint2* h2 = reinterpret_cast<const uint2*>(g16 + off);
         const int nv = int(len >> 2);
         float part = 0.f;  // one chunk is at most 64 K elements: 64 fp32 terms per thread, then fp64
         for (int i = threadIdx.x; i < nv; i += blockDim.x) {
-            const float4 q = __ldg(g4 + i);
+            float4 q;
+            if (g16) {
+                const uint2 h = __ldg(h2 + i);
+                q = make_float4(bf16_lo(h.x), bf16_hi(h.x), bf16_lo(h.y), bf16_hi(h.y));
+            } else {
+                q = __ldg(g4 + i);
+            }
             part += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
         }
         acc += double(part);
@@ -146,10 +162,10 @@ extern "C" {
 
 static int chunk_grid(int n_chunks) { return std::max(1, std::min(n_chunks, device_sm_count() * 8)); }
 
-int t2v_sqnorm_chunks(const float* g, const int64_t* chunks, int32_t n_chunks, double* out, void* stream) {
+int t2v_sqnorm_chunks(const float* g, const void* g_bf16, const int64_t* chunks, int32_t n_chunks, double* out, void* stream) {
     if (n_chunks <= 0) return 0;
     const int rc = int(launch_pdl(sqnorm_chunks_kernel, dim3(chunk_grid(n_chunks)), dim3(256), size_t(0), static_cast<cudaStream_t>(stream), g,
-                                  chunks, int(n_chunks), out));
+                                  chunks, int(n_chunks), out, static_cast<const __nv_bfloat16*>(g_bf16)));
     return launch_checked(rc, "sqnorm_chunks");
 }
 
@@ -160,14 +176,15 @@ int t2v_adamw_prepare(const float* hp_in, float* hp, int32_t n_sets, int64_t* st
     return launch_checked(rc, "adamw_prepare");
 }
 
-int t2v_adamw_chunks(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_t n_shadow, const int64_t* chunks, int32_t n_chunks,
-                     const float* hp, int32_t zero_grad, void* stream) {
+int t2v_adamw_chunks(float* p, float* g, const void* g_bf16, float* m, float* v, void* shadow_bf16, int64_t n_shadow, const int64_t* chunks,
+                     int32_t n_chunks, const float* hp, int32_t zero_grad, void* stream) {
     if (n_chunks <= 0) return 0;
     if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15u)
         return fail(-2, "adamw_chunks: p, g, m, v must be 16-byte aligned");
     if (shadow_bf16 && (reinterpret_cast<uintptr_t>(shadow_bf16) & 7u)) return fail(-2, "adamw_chunks: shadow must be 8-byte aligned");
     const int rc = int(launch_pdl(adamw_chunks_kernel, dim3(chunk_grid(n_chunks)), dim3(256), size_t(0), static_cast<cudaStream_t>(stream), p, g, m,
-                                  v, static_cast<__nv_bfloat16*>(shadow_bf16), n_shadow, chunks, int(n_chunks), hp, int(zero_grad)));
+                                  v, static_cast<__nv_bfloat16*>(shadow_bf16), n_shadow, chunks, int(n_chunks), hp, int(zero_grad),
+                                  static_cast<const __nv_bfloat16*>(g_bf16)));
     return launch_checked(rc, "adamw_chunks");
 }
 

@@ -109,15 +109,17 @@ class FusedAdamW(torch.optim.Optimizer):
             self.hp_host[i, 3], self.hp_host[i, 4] = float(g["eps"]), float(g["weight_decay"])
         self.hp_in.copy_(self.hp_host, non_blocking=True)
 
-    def launch(self, zero_grad=True):
-        """The device-only part of one step (capturable): gradient norm, scalars, update."""
+    def launch(self, zero_grad=True, grad_bf16=None):
+        """The device-only part of one step (capturable): gradient norm, scalars, update.  grad_bf16: flat bf16 twin of the
+        gradient buffer holding the all-reduced gradients (runtime.GradientBuckets.comm); the fp32 buffer is then only zeroed."""
         ar = self.arena
         if self.max_grad_norm is not None:
             for s in self._sets:
-                prims.sqnorm_chunks(ar.grad, s["chunks"], self.sq)
+                prims.sqnorm_chunks(ar.grad, s["chunks"], self.sq, grad_bf16)
         prims.adamw_prepare(self.hp_in, self.hp, self.state_dev, self.sq, self.max_grad_norm or 0.0)
         for i, s in enumerate(self._sets):
-            prims.adamw_chunks(ar.master, ar.grad, self.exp_avg, self.exp_avg_sq, ar.shadow, ar.n_mat, s["chunks"], self.hp[i], zero_grad)
+            prims.adamw_chunks(ar.master, ar.grad, self.exp_avg, self.exp_avg_sq, ar.shadow, ar.n_mat, s["chunks"], self.hp[i], zero_grad,
+                               grad_bf16)
 
     @torch.no_grad()
     def step(self, closure=None, zero_grad=True):

@@ -320,11 +320,12 @@ def counter_add(counter, value=1):
     native.check(native.lib().t2v_counter_add(_p(counter), int(value), _stream()))
 
 
-def sqnorm_chunks(g, chunks, out):
-    """out[0] (fp64) += sum of g^2 over the (offset, length) chunks of the flat fp32 buffer g."""
+def sqnorm_chunks(g, chunks, out, g_bf16=None):
+    """out[0] (fp64) += sum of g^2 over the (offset, length) chunks of the flat fp32 buffer g (or of its bf16 twin g_bf16)."""
     _chk_f32(g)
+    _chk_bf16(g_bf16)
     assert chunks.dtype == torch.int64 and out.dtype == torch.float64
-    native.check(native.lib().t2v_sqnorm_chunks(_p(g), _p(chunks), chunks.shape[0], _p(out), _stream()))
+    native.check(native.lib().t2v_sqnorm_chunks(_p(g), _p(g_bf16), _p(chunks), chunks.shape[0], _p(out), _stream()))
 
 
 def adamw_prepare(hp_in, hp, state, sq, max_norm):
@@ -334,12 +335,28 @@ def adamw_prepare(hp_in, hp, state, sq, max_norm):
     native.check(native.lib().t2v_adamw_prepare(_p(hp_in), _p(hp), hp_in.shape[0], _p(state), _p(sq), float(max_norm or 0.0), _stream()))
 
 
-def adamw_chunks(p, g, m, v, shadow, n_shadow, chunks, hp_row, zero_grad=True):
-    """Fused AdamW over the chunk table of one hyper-parameter set; hp_row: the set's 8 floats on the device."""
+def adamw_chunks(p, g, m, v, shadow, n_shadow, chunks, hp_row, zero_grad=True, g_bf16=None):
+    """Fused AdamW over the chunk table of one hyper-parameter set; hp_row: the set's 8 floats on the device.  g_bf16: read
+    the gradient values from this bf16 twin of g (all-reduced gradients) - g itself is then only zeroed."""
     _chk_f32(p, g, m, v, hp_row)
-    _chk_bf16(shadow)
-    native.check(native.lib().t2v_adamw_chunks(_p(p), _p(g), _p(m), _p(v), _p(shadow), int(n_shadow), _p(chunks), chunks.shape[0], _p(hp_row),
-                                               int(bool(zero_grad)), _stream()))
+    _chk_bf16(shadow, g_bf16)
+    native.check(native.lib().t2v_adamw_chunks(_p(p), _p(g), _p(g_bf16), _p(m), _p(v), _p(shadow), int(n_shadow), _p(chunks), chunks.shape[0],
+                                               _p(hp_row), int(bool(zero_grad)), _stream()))
+
+
+def scale_cast_f32_bf16(src, dst, alpha):
+    """dst (bf16) = alpha * src (fp32): gradient compression before the data-parallel all-reduce."""
+    _chk_f32(src)
+    _chk_bf16(dst)
+    assert src.numel() == dst.numel()
+    native.check(native.lib().t2v_scale_cast_f32_bf16(_p(src), _p(dst), src.numel(), float(alpha), _stream()))
+
+
+def cast_bf16_f32(src, dst):
+    _chk_bf16(src)
+    _chk_f32(dst)
+    assert src.numel() == dst.numel()
+    native.check(native.lib().t2v_cast_bf16_f32(_p(src), _p(dst), src.numel(), _stream()))
 
 
 def add_f32(a, b):

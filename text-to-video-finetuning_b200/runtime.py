@@ -8,6 +8,8 @@ B200-first design notes
     the reference reaches NCCL implicitly through accelerate/DDP, train.py:661,861).
   * A step has ~4-5 thousand kernel launches; replaying it as a CUDA graph removes the host launch cost entirely.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -31,16 +33,24 @@ class ParamArena:
         for p in params:
             if p.dtype != torch.float32:
                 raise ValueError("ParamArena expects fp32 master parameters (the reference keeps the UNet in fp32 under autocast)")
-        # matrices first (they need a bf16 shadow), then vectors; trainable and frozen alike
+        # matrices first (they need a bf16 shadow), then vectors; inside each class the TRAINABLE parameters come first (in
+        # registration order), so the gradients that have to cross NVLink form two compact spans - 29 M elements instead of
+        # 1.44 B for a LoRA run - and a block's trainable matrices stay one contiguous range.
         mats = [p for p in params if p.dim() >= 2]
         vecs = [p for p in params if p.dim() < 2]
+        mats = [p for p in mats if p.requires_grad] + [p for p in mats if not p.requires_grad]
+        vecs = [p for p in vecs if p.requires_grad] + [p for p in vecs if not p.requires_grad]
         self.params = mats + vecs
+        self._flags = [p.requires_grad for p in self.params]
         offs, off = [], 0
         for p in self.params:
             offs.append(off)
             off += _align(p.numel())
         self.total = off
         self.n_mat = sum(_align(p.numel()) for p in mats)
+        t_mat = sum(_align(p.numel()) for p in mats if p.requires_grad)
+        t_vec = sum(_align(p.numel()) for p in vecs if p.requires_grad)
+        self.trainable_spans = [(0, t_mat), (self.n_mat, self.n_mat + t_vec)]   # what a data-parallel step has to all-reduce
         self.master = torch.zeros(self.total, device=device, dtype=torch.float32)
         self.grad = torch.zeros(self.total, device=device, dtype=torch.float32)
         self.shadow = torch.zeros(max(self.n_mat, 8), device=device, dtype=torch.bfloat16)
@@ -107,35 +117,53 @@ class ParamArena:
     def grad_norm(self):
         return self.grad.norm()
 
+    def check_layout(self):
+        """The trainable-first layout is fixed when the arena is built; flipping requires_grad afterwards needs a new arena."""
+        if any(p.requires_grad != f for p, f in zip(self.params, self._flags)):
+            raise RuntimeError("requires_grad changed after the parameter arena was built: rebuild the DataParallelStep")
+
 
 def allreduce_gradients(arena, world_size=None, average=True):
-    """The one collective of the step: all-reduce the flat fp32 gradient buffer over NCCL (NVLink 5 / NVSwitch)."""
+    """The one collective of the step, un-overlapped form (T2V_NO_OVERLAP=1): all-reduce the trainable spans of the flat
+    fp32 gradient buffer over NCCL (NVLink 5 / NVSwitch)."""
     if not (dist.is_available() and dist.is_initialized()):
         return None
     world_size = world_size or dist.get_world_size()
     if world_size == 1:
         return None
-    if average:
-        arena.grad.div_(world_size)
-    return dist.all_reduce(arena.grad, op=dist.ReduceOp.SUM, async_op=False)
+    for lo, hi in arena.trainable_spans:
+        if hi > lo:
+            view = arena.grad[lo:hi]
+            if average:
+                view.div_(world_size)
+            dist.all_reduce(view, op=dist.ReduceOp.SUM, async_op=False)
+    return None
 
 
 class GradientBuckets:
     """Overlaps the gradient all-reduce with the backward pass.
 
-    The flat gradient buffer holds the weight matrices in registration order, so the matrices of one top-level block
+    The flat gradient buffer holds the trainable weight matrices in registration order, so those of one top-level block
     (down_blocks.i / mid_block / up_blocks.i) are one contiguous range.  The model marks the input of every block
-    (ops.grad_mark); when the backward pass reaches a mark, that block's range is complete and its all-reduce is
-    issued asynchronously (NCCL runs it on its own stream, also inside a captured CUDA graph) while the rest of the
-    backward keeps the SMs busy.  `finish()` reduces what is left (stem, time embedding, all vectors) and joins."""
+    (ops.grad_mark); when the backward pass reaches a mark, that block's range is complete and its all-reduce is issued
+    asynchronously (NCCL runs it on its own stream, also inside a captured CUDA graph) while the rest of the backward keeps
+    the SMs busy.  `finish()` reduces what is left of the trainable spans (stem, time embedding, all vectors) and joins.
 
-    def __init__(self, arena, module, group=None):
+    compress (default on NCCL): gradients cross NVLink as bf16.  Each range is scaled by 1 / world and rounded into a flat
+    bf16 twin of the gradient buffer (one pass, 6 B / parameter, overlapped like the collective itself), the SUM all-reduce
+    runs on that twin - half the bytes on the wire - and the fused AdamW reads its gradient values straight from it
+    (optim.FusedAdamW.launch(grad_bf16=...)), so nothing is widened back.  Accumulation across micro-steps stays fp32.
+    Pieces of at most PIECE elements keep every collective short enough to pipeline behind the next block's backward."""
+
+    PIECE = 1 << 26   # 64 Mi elements = 128 MiB of bf16 per collective
+
+    def __init__(self, arena, module, group=None, compress=None):
         self.arena, self.module, self.group = arena, module, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         off_of = {id(p): o for p, o in zip(arena.params, arena.offsets)}
         ranges = {}
         for name, p in module.named_parameters():
-            if p.dim() < 2 or id(p) not in off_of:
+            if p.dim() < 2 or id(p) not in off_of or not p.requires_grad:
                 continue
             parts = name.split(".")
             key = ".".join(parts[:2]) if parts[0] in ("down_blocks", "up_blocks") else parts[0]
@@ -149,37 +177,65 @@ class GradientBuckets:
                 raise RuntimeError("block gradient ranges overlap: parameters are not laid out in registration order")
         self.armed = False
         self._done, self._works = set(), []
-        use_avg = dist.is_initialized() and dist.get_backend(group) == "nccl"
-        self._op = dist.ReduceOp.AVG if use_avg else dist.ReduceOp.SUM
+        nccl = dist.is_initialized() and dist.get_backend(group) == "nccl"
+        if compress is None and os.environ.get("T2V_GRAD_COMPRESS") is not None:   # A/B switch: 0 = fp32 on the wire
+            compress = os.environ["T2V_GRAD_COMPRESS"] not in ("0", "")
+        self.compress = nccl if compress is None else bool(compress)
+        self.comm = torch.zeros(arena.total, device=arena.grad.device, dtype=torch.bfloat16) if self.compress else None
+        self._op = dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM
+        self.bytes_on_wire = 0   # per-rank payload handed to the collectives of the last step
 
     def install(self):
         self.module._t2v_grad_hook = self.on_block_done
 
     def _reduce(self, a, b):
-        if b <= a:
-            return
-        view = self.arena.grad[a:b]
-        if self._op == dist.ReduceOp.SUM:
-            view.div_(self.world)
-        self._works.append(dist.all_reduce(view, op=self._op, group=self.group, async_op=True))
+        while a < b:
+            e = min(b, a + self.PIECE)
+            if self.compress:
+                view = self.comm[a:e]
+                prims.scale_cast_f32_bf16(self.arena.grad[a:e], view, 1.0 / self.world)
+                self._works.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            else:
+                view = self.arena.grad[a:e]
+                if self._op == dist.ReduceOp.SUM:
+                    view.div_(self.world)
+                self._works.append(dist.all_reduce(view, op=self._op, group=self.group, async_op=True))
+            self.bytes_on_wire += view.numel() * view.element_size()
+            a = e
 
     def on_block_done(self, key):
         if not self.armed or key in self._done or key not in self.ranges:
             return
+        if not self._done:
+            self.bytes_on_wire = 0
         self._done.add(key)
         self._reduce(*self.ranges[key])
 
     def finish(self):
-        """Reduce every range no mark has covered, then make the current stream wait for all of it."""
+        """Reduce every part of the trainable spans no mark has covered, then make the current stream wait for all of it."""
+        if not self._done:
+            self.bytes_on_wire = 0
         covered = sorted(self.ranges[k] for k in self._done)
-        pos = 0
-        for a, b in covered + [(self.arena.total, self.arena.total)]:
-            self._reduce(pos, a)
-            pos = max(pos, b)
+        for lo, hi in self.arena.trainable_spans:
+            pos = lo
+            for a, b in covered + [(hi, hi)]:
+                a, b = max(a, lo), min(b, hi)
+                if a > pos:
+                    self._reduce(pos, min(a, hi))
+                pos = max(pos, b)
+                if pos >= hi:
+                    break
         for w in self._works:
             w.wait()
         self.last_overlapped = len(self._done)   # blocks whose all-reduce started inside the backward pass
         self._works, self._done, self.armed = [], set(), False
+
+    def widen(self):
+        """compress mode without a fused optimizer: write the reduced gradients back into the fp32 buffer."""
+        if self.compress:
+            for lo, hi in self.arena.trainable_spans:
+                if hi > lo:
+                    prims.cast_bf16_f32(self.comm[lo:hi], self.arena.grad[lo:hi])
 
 
 class GraphedStep:

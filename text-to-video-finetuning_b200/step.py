@@ -102,16 +102,22 @@ class DataParallelStep:
                 self.buckets.armed = i == self.passes - 1   # gradients are final only in the last pass
             loss.backward(self._gscale if self.accumulation > 1 else None)
             total = loss.detach() if total is None else total + loss.detach()
+        comm = None
         if overlap:
             self.buckets.finish()
+            if fused:
+                comm = self.buckets.comm          # bf16 all-reduced gradients: the update reads them directly
+            else:
+                self.buckets.widen()              # a torch optimizer / a test wants them in param.grad (fp32)
         elif reduce_now and self.arena is not None:
             allreduce_gradients(self.arena)
         if fused and last:
-            self.optimizer.launch(zero_grad=True)
+            self.optimizer.launch(zero_grad=True, grad_bf16=comm)
         return total
 
     def __call__(self, latents, noise, timesteps, encoder_hidden_states):
         if self.arena is not None:
+            self.arena.check_layout()
             self.arena.reattach_grads()
         first = self._micro % self.accumulation == 0
         last = (self._micro + 1) % self.accumulation == 0
