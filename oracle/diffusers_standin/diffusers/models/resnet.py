@@ -1,10 +1,7 @@
+"""Stand-in for diffusers.models.resnet as plain nn.Modules on torch's own operators; independent of oracle/leaves.py
+(see embeddings.py)."""
 import torch.nn as nn
-
-from oracle import leaves as L
-
-
-def _params(m):
-    return dict(m.named_parameters())
+import torch.nn.functional as F
 
 
 class ResnetBlock2D(nn.Module):
@@ -12,13 +9,12 @@ class ResnetBlock2D(nn.Module):
                  groups_out=None, pre_norm=True, eps=1e-6, non_linearity="swish", time_embedding_norm="default",
                  output_scale_factor=1.0, use_in_shortcut=None, **unused):
         super().__init__()
-        assert time_embedding_norm == "default" and dropout == 0.0 and non_linearity in ("swish", "silu")
+        assert time_embedding_norm == "default" and non_linearity in ("swish", "silu")
         out_channels = in_channels if out_channels is None else out_channels
-        self.groups, self.eps, self.osf = groups, eps, output_scale_factor
+        self.output_scale_factor = output_scale_factor
         self.norm1 = nn.GroupNorm(groups, in_channels, eps=eps)
         self.conv1 = nn.Conv2d(in_channels, out_channels, 3, padding=1)
-        if temb_channels is not None:
-            self.time_emb_proj = nn.Linear(temb_channels, out_channels)
+        self.time_emb_proj = nn.Linear(temb_channels, out_channels) if temb_channels is not None else None
         self.norm2 = nn.GroupNorm(groups_out or groups, out_channels, eps=eps)
         self.dropout = nn.Dropout(dropout)
         self.conv2 = nn.Conv2d(out_channels, out_channels, 3, padding=1)
@@ -27,10 +23,18 @@ class ResnetBlock2D(nn.Module):
         self.conv_shortcut = nn.Conv2d(in_channels, out_channels, 1) if use_in_shortcut else None
 
     def forward(self, input_tensor, temb=None):
-        return L.resnet_block2d(_params(self), "", input_tensor, temb, self.groups, self.eps, self.osf)
+        h = self.conv1(self.nonlinearity(self.norm1(input_tensor)))
+        if temb is not None and self.time_emb_proj is not None:
+            h = h + self.time_emb_proj(self.nonlinearity(temb))[:, :, None, None]
+        h = self.conv2(self.dropout(self.nonlinearity(self.norm2(h))))
+        if self.conv_shortcut is not None:
+            input_tensor = self.conv_shortcut(input_tensor)
+        return (input_tensor + h) / self.output_scale_factor
 
 
 class TemporalConvLayer(nn.Module):
+    """(b f) c h w -> b c f h w; four GroupNorm(32) - SiLU - [Dropout] - Conv3d(3,1,1) stages; + identity; back."""
+
     def __init__(self, in_dim, out_dim=None, dropout=0.0):
         super().__init__()
         out_dim = out_dim or in_dim
@@ -42,9 +46,11 @@ class TemporalConvLayer(nn.Module):
         nn.init.zeros_(self.conv4[-1].bias)
 
     def forward(self, hidden_states, num_frames=1):
-        assert not self.training or all(m.p == 0 for m in self.modules() if isinstance(m, nn.Dropout)), \
-            "oracle runs with dropout disabled (eval_train / p=0)"
-        return L.temporal_conv_layer(_params(self), "", hidden_states, num_frames)
+        hidden_states = hidden_states[None, :].reshape((-1, num_frames) + hidden_states.shape[1:]).permute(0, 2, 1, 3, 4)
+        identity = hidden_states
+        hidden_states = self.conv4(self.conv3(self.conv2(self.conv1(hidden_states))))
+        hidden_states = identity + hidden_states
+        return hidden_states.permute(0, 2, 1, 3, 4).reshape((hidden_states.shape[0] * hidden_states.shape[2], -1) + hidden_states.shape[3:])
 
 
 class Downsample2D(nn.Module):
@@ -55,7 +61,9 @@ class Downsample2D(nn.Module):
         self.conv = nn.Conv2d(channels, out_channels or channels, 3, stride=2, padding=padding)
 
     def forward(self, hidden_states):
-        return L.downsample2d(_params(self), "", hidden_states, self.padding)
+        if self.padding == 0:
+            hidden_states = F.pad(hidden_states, (0, 1, 0, 1), mode="constant", value=0)
+        return self.conv(hidden_states)
 
 
 class Upsample2D(nn.Module):
@@ -65,4 +73,8 @@ class Upsample2D(nn.Module):
         self.conv = nn.Conv2d(channels, out_channels or channels, 3, padding=1)
 
     def forward(self, hidden_states, output_size=None):
-        return L.upsample2d(_params(self), "", hidden_states, output_size)
+        if output_size is None:
+            hidden_states = F.interpolate(hidden_states, scale_factor=2.0, mode="nearest")
+        else:
+            hidden_states = F.interpolate(hidden_states, size=output_size, mode="nearest")
+        return self.conv(hidden_states)

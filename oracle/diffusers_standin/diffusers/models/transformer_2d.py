@@ -1,9 +1,10 @@
+"""Stand-in for diffusers.models.transformer_2d (linear-projection variant) as a plain nn.Module; independent of
+oracle/leaves.py (see embeddings.py)."""
 from dataclasses import dataclass
 
 import torch
 import torch.nn as nn
 
-from oracle import leaves as L
 from ..utils import BaseOutput
 from .attention import BasicTransformerBlock
 
@@ -21,7 +22,6 @@ class Transformer2DModel(nn.Module):
         super().__init__()
         assert use_linear_projection and num_layers == 1 and not only_cross_attention
         inner = num_attention_heads * attention_head_dim
-        self.heads, self.groups = num_attention_heads, norm_num_groups
         self.norm = nn.GroupNorm(norm_num_groups, in_channels, eps=1e-6)
         self.proj_in = nn.Linear(in_channels, inner)
         self.transformer_blocks = nn.ModuleList(
@@ -30,5 +30,14 @@ class Transformer2DModel(nn.Module):
 
     def forward(self, hidden_states, encoder_hidden_states=None, timestep=None, class_labels=None,
                 cross_attention_kwargs=None, attention_mask=None, return_dict=True):
-        out = L.transformer2d(dict(self.named_parameters()), "", hidden_states, encoder_hidden_states, self.heads, self.groups)
+        batch, channels, height, width = hidden_states.shape
+        residual = hidden_states
+        hidden_states = self.norm(hidden_states)
+        hidden_states = hidden_states.permute(0, 2, 3, 1).reshape(batch, height * width, channels)
+        hidden_states = self.proj_in(hidden_states)
+        for block in self.transformer_blocks:
+            hidden_states = block(hidden_states, encoder_hidden_states=encoder_hidden_states)
+        hidden_states = self.proj_out(hidden_states)
+        hidden_states = hidden_states.reshape(batch, height, width, channels).permute(0, 3, 1, 2).contiguous()
+        out = hidden_states + residual
         return Transformer2DModelOutput(sample=out) if return_dict else (out,)

@@ -61,7 +61,7 @@ def main():
         out = dict(cfg=c["cfg"], seed=c["seed"], latents=lat, noise=noise, timesteps=t, text=ehs, pred=pred.detach(),
                    loss=loss.detach(), grad_norms={n: g_.norm().item() if g_ is not None else None for n, g_ in grads.items()},
                    grads={n: grads[n].detach().clone() for n in KEEP_FULL if grads.get(n) is not None and grads[n].numel() < 40000},
-                   source="reference models/unet_3d_condition.py + models/unet_3d_blocks.py (unmodified) over oracle/diffusers_standin, fp32 CPU")
+                   source="reference models/unet_3d_condition.py + models/unet_3d_blocks.py (unmodified) over oracle/diffusers_standin (plain nn.Modules on torch operators, independent of oracle/leaves.py), fp32 CPU")
         path = os.path.join(ROOT, "tests", "golden", name + ".pt")
         torch.save(out, path)
         print(name, "loss", loss.item(), os.path.getsize(path) // 1024, "KiB")
