@@ -188,6 +188,17 @@ int t2v_add_bf16(const void* a, const void* b, const void* c, void* out, int64_t
 int t2v_scale_bf16(const void* a, void* out, int64_t n, float alpha, void* stream);
 int t2v_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream);
 int t2v_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* Frozen CLIP text encoder (train.py:784-790 `text_encoder(token_ids)[0]`) - the two ops it needs beyond
+ * the shared GEMM / LayerNorm / softmax kernels: token + position embedding lookup (fp32 tables -> bf16 [rows][C], rows =
+ * B * L) and the MLP activation (quick = 0: exact GELU as in the OpenCLIP ViT-H text tower of ms-1.7b; 1: quick_gelu).
+ * t2v_softmax_fwd's causal_period > 0 applies the encoder's causal mask (row r sees columns <= r % causal_period).         */
+int t2v_embed_tokens(const int64_t* ids, const float* tok_emb, const float* pos_emb, void* out, int64_t rows, int32_t L, int32_t C,
+                     int32_t vocab, void* stream);
+int t2v_gelu_bf16(const void* x, void* y, int64_t n, int32_t quick, void* stream);
+/* Data pipeline front end (reference utils/dataset.py:22-41 normalize_input after the video reader's resize): decoded RGB
+ * frames uint8 [F][H0][W0][3] -> bilinear resize to h x w (half-pixel centres) -> x / 127.5 - 1 -> bf16 channels-last
+ * [F][h][w][8] (channels 3..7 zero), the layout AutoencoderKL.encode consumes.                                          */
+int t2v_frames_u8_to_nhwc8(const uint8_t* src, void* dst, int32_t F, int32_t H0, int32_t W0, int32_t h, int32_t w, void* stream);
 /* Gradient compression around the data-parallel all-reduce (the reference reduces through accelerate/DDP, train.py:661,861):
  * dst (bf16) = alpha * src (fp32), alpha = 1 / world so that a SUM all-reduce averages; and the widening inverse.          */
 int t2v_scale_cast_f32_bf16(const float* src, void* dst, int64_t n, float alpha, void* stream);
@@ -214,7 +225,8 @@ int t2v_colsum(const void* x, float* out, int32_t S, int64_t P, int32_t C, void*
 int t2v_colsum_f32(const float* x, float* out, int32_t S, int32_t C, void* stream);
 /* Row softmax between the two attention GEMMs: fp32 scores [rows][ld_in] -> bf16 probabilities [rows][ld_out]
  * (columns >= n_valid written as 0), and dS = P * (dP - rowsum(P dP)) * scale.                                     */
-int t2v_softmax_fwd(const float* s, void* p, int64_t rows, int32_t n_valid, int32_t ld_in, int32_t ld_out, void* stream);
+int t2v_softmax_fwd(const float* s, void* p, int64_t rows, int32_t n_valid, int32_t ld_in, int32_t ld_out, int32_t causal_period,
+                    void* stream);
 int t2v_softmax_bwd(const void* p, const float* dp, void* ds, int64_t rows, int32_t n_valid, int32_t ld_p, int32_t ld_dp, float scale,
                     void* stream);
 /* Timesteps(dim, flip_sin_to_cos=True, shift 0) (unet_3d_condition.py:138,392): int64 [B] -> bf16 [B][dim] = [cos | sin]. */

@@ -342,8 +342,30 @@ def colsum_f32(x, out):
     out += x.sum(0)
 
 
-def softmax_fwd(s, n_valid, ld_out):
-    p = torch.softmax(s[..., :n_valid].float(), dim=-1)
+def frames_u8_to_nhwc8(frames, out_hw):
+    x = frames.permute(0, 3, 1, 2).float()
+    if tuple(x.shape[-2:]) != tuple(out_hw):
+        x = F.interpolate(x, size=tuple(out_hw), mode="bilinear", align_corners=False)
+    x = (x / 127.5 - 1.0).permute(0, 2, 3, 1)
+    return torch.cat([x, torch.zeros(x.shape[:-1] + (5,), device=x.device)], dim=-1).to(BF).contiguous()
+
+
+def gelu_bf16(x, quick=False):
+    xf = x.float()
+    return (xf * torch.sigmoid(1.702 * xf) if quick else F.gelu(xf)).to(BF)
+
+
+def embed_tokens(ids, tok_emb, pos_emb):
+    B, Lq = ids.shape
+    return (tok_emb[ids] + pos_emb[:Lq][None]).reshape(B * Lq, -1).to(BF)
+
+
+def softmax_fwd(s, n_valid, ld_out, causal_period=0):
+    sc = s[..., :n_valid].float()
+    if causal_period:
+        rows = torch.arange(sc.numel() // sc.shape[-1], device=s.device).view(sc.shape[:-1]) % causal_period
+        sc = sc.masked_fill(torch.arange(n_valid, device=s.device) > rows[..., None], float("-inf"))
+    p = torch.softmax(sc, dim=-1)
     out = torch.zeros(s.shape[:-1] + (ld_out,), dtype=BF, device=s.device)
     out[..., :n_valid] = p.to(BF)
     return out

@@ -131,6 +131,34 @@ __global__ void geglu_fwd_kernel(const __nv_bfloat16* __restrict__ proj, __nv_bf
         reinterpret_cast<uint4*>(out)[i] = pack8e(h);
     }
 }
+// y = gelu(x) (exact erf form, or CLIP's quick_gelu x * sigmoid(1.702 x)): the MLP activation of the frozen text encoder
+__global__ void gelu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t nvec, int quick) {
+    pdl_sync();
+    GRID_STRIDE(i, nvec) {
+        float v[8];
+        unpack8e(__ldg(reinterpret_cast<const uint4*>(x) + i), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = quick ? v[j] / (1.f + __expf(-1.702f * v[j])) : v[j] * gelu_erf(v[j]);
+        reinterpret_cast<uint4*>(y)[i] = pack8e(v);
+    }
+}
+// out[b*L + l][:] = tok_emb[ids[b][l]][:] + pos_emb[l][:]   (fp32 tables -> bf16 activations; CLIPTextEmbeddings)
+__global__ void embed_tokens_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tok, const float* __restrict__ pos,
+                                    __nv_bfloat16* __restrict__ out, int64_t rows, int L, int C, int vocab) {
+    pdl_sync();
+    const int V = C >> 3;
+    GRID_STRIDE(i, rows * V) {
+        const int64_t r = i / V;
+        const int cv = int(i % V);
+        int64_t id = ids[r];
+        id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+        const float4* t4 = reinterpret_cast<const float4*>(tok + id * C) + 2 * cv;
+        const float4* p4 = reinterpret_cast<const float4*>(pos + (r % L) * C) + 2 * cv;
+        const float4 a = __ldg(t4), b = __ldg(t4 + 1), c = __ldg(p4), d = __ldg(p4 + 1);
+        const float v[8] = {a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w, b.x + d.x, b.y + d.y, b.z + d.z, b.w + d.w};
+        reinterpret_cast<uint4*>(out)[i] = pack8e(v);
+    }
+}
 __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ proj, const __nv_bfloat16* __restrict__ dout,
                                  __nv_bfloat16* __restrict__ dproj, int64_t M, int I) {
     pdl_sync();
@@ -231,6 +259,33 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
         reinterpret_cast<uint4*>(dst)[i] = pack8e(v);
     }
     if (blockIdx.x == 0 && threadIdx.x < (n & 7)) dst[(nv << 3) + threadIdx.x] = __float2bfloat16_rn(src[(nv << 3) + threadIdx.x]);
+}
+
+// Data pipeline (reference utils/dataset.py:22-41 normalize_input + the decoder's resize): decoded RGB frames
+// uint8 [F][H0][W0][3] -> bilinear resize (half-pixel centres, as F.interpolate(align_corners=False)) -> x / 127.5 - 1 ->
+// bf16 channels-last [F][h][w][8] (channels 3..7 zero): exactly the tensor AutoencoderKL.encode consumes, in one pass.
+__global__ void frames_u8_to_nhwc8_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ dst, int F, int H0, int W0, int h, int w) {
+    pdl_sync();
+    const int64_t total = int64_t(F) * h * w;
+    const float sy = float(H0) / float(h), sx = float(W0) / float(w);
+    GRID_STRIDE(i, total) {
+        const int x = int(i % w), y = int((i / w) % h);
+        const int f = int(i / (int64_t(w) * h));
+        const float fy = fmaxf((y + 0.5f) * sy - 0.5f, 0.f), fx = fmaxf((x + 0.5f) * sx - 0.5f, 0.f);
+        const int y0 = min(int(fy), H0 - 1), x0 = min(int(fx), W0 - 1);
+        const int y1 = min(y0 + 1, H0 - 1), x1 = min(x0 + 1, W0 - 1);
+        const float wy = fy - float(y0), wx = fx - float(x0);
+        const uint8_t* base = src + int64_t(f) * H0 * W0 * 3;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float p00 = base[(int64_t(y0) * W0 + x0) * 3 + c], p01 = base[(int64_t(y0) * W0 + x1) * 3 + c];
+            const float p10 = base[(int64_t(y1) * W0 + x0) * 3 + c], p11 = base[(int64_t(y1) * W0 + x1) * 3 + c];
+            const float top = p00 + (p01 - p00) * wx, bot = p10 + (p11 - p10) * wx;
+            v[c] = (top + (bot - top) * wy) * (1.0f / 127.5f) - 1.0f;
+        }
+        reinterpret_cast<uint4*>(dst)[i] = pack8e(v);
+    }
 }
 
 // Gradient compression for the data-parallel all-reduce: dst (bf16) = alpha * src (fp32); and its inverse (widening).
@@ -369,13 +424,15 @@ __global__ void colsum_f32_kernel(const float* __restrict__ x, float* __restrict
 }
 
 // Row softmax over fp32 scores -> bf16 probabilities; columns >= n_valid (padding up to ld_out) are written as 0.
-__global__ void softmax_fwd_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, int64_t rows, int n_valid, int ld_in,
-                                   int ld_out) {
+// causal_period > 0: row r attends to columns <= r % causal_period (CLIP text encoder's causal mask).
+__global__ void softmax_fwd_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, int64_t rows, int n_valid_all, int ld_in,
+                                   int ld_out, int causal_period) {
     pdl_sync();
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
     const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
     for (int64_t r = warp; r < rows; r += nwarps) {
+        const int n_valid = causal_period > 0 ? min(n_valid_all, int(r % causal_period) + 1) : n_valid_all;
         const float* sr = s + r * ld_in;
         float mx = -INFINITY;
         for (int c = lane; c < n_valid; c += 32) mx = fmaxf(mx, sr[c]);
@@ -512,6 +569,22 @@ int t2v_geglu_bwd(const void* proj, const void* dout, void* dproj, int64_t M, in
     launch_pdl(geglu_bwd_kernel, dim3(ew_grid(M * (I / 8))), dim3(256), size_t(0), ST, BF(proj), BF(dout), BFW(dproj), M, I);
     return launch_checked(int(cudaGetLastError()), "geglu_bwd");
 }
+int t2v_frames_u8_to_nhwc8(const uint8_t* src, void* dst, int32_t F, int32_t H0, int32_t W0, int32_t h, int32_t w, void* stream) {
+    if (F <= 0 || H0 <= 0 || W0 <= 0 || h <= 0 || w <= 0) return fail(-2, "frames_u8_to_nhwc8: bad shape");
+    launch_pdl(frames_u8_to_nhwc8_kernel, dim3(ew_grid(int64_t(F) * h * w)), dim3(256), size_t(0), ST, src, BFW(dst), F, H0, W0, h, w);
+    return launch_checked(int(cudaGetLastError()), "frames_u8_to_nhwc8");
+}
+int t2v_gelu_bf16(const void* x, void* y, int64_t n, int32_t quick, void* stream) {
+    if (n % 8) return fail(-2, "gelu: n must be a multiple of 8");
+    launch_pdl(gelu_kernel, dim3(ew_grid(n / 8)), dim3(256), size_t(0), ST, BF(x), BFW(y), n / 8, quick);
+    return launch_checked(int(cudaGetLastError()), "gelu_bf16");
+}
+int t2v_embed_tokens(const int64_t* ids, const float* tok_emb, const float* pos_emb, void* out, int64_t rows, int32_t L, int32_t C,
+                     int32_t vocab, void* stream) {
+    if (C % 8) return fail(-2, "embed_tokens: C=%d must be a multiple of 8", C);
+    launch_pdl(embed_tokens_kernel, dim3(ew_grid(rows * (C / 8))), dim3(256), size_t(0), ST, ids, tok_emb, pos_emb, BFW(out), rows, L, C, vocab);
+    return launch_checked(int(cudaGetLastError()), "embed_tokens");
+}
 int t2v_silu_f32_to_bf16(const float* x, void* y, int64_t n, int32_t apply_silu, void* stream) {
     launch_pdl(silu_f32_to_bf16_kernel, dim3(ew_grid(n)), dim3(256), size_t(0), ST, x, BFW(y), n, apply_silu);
     return launch_checked(int(cudaGetLastError()), "silu_f32_to_bf16");
@@ -592,9 +665,10 @@ int t2v_colsum_f32(const float* x, float* out, int32_t S, int32_t C, void* strea
     launch_pdl(colsum_f32_kernel, dim3(ew_grid(C)), dim3(256), size_t(0), ST, x, out, S, C);
     return launch_checked(int(cudaGetLastError()), "colsum_f32");
 }
-int t2v_softmax_fwd(const float* s, void* p, int64_t rows, int32_t n_valid, int32_t ld_in, int32_t ld_out, void* stream) {
+int t2v_softmax_fwd(const float* s, void* p, int64_t rows, int32_t n_valid, int32_t ld_in, int32_t ld_out, int32_t causal_period,
+                    void* stream) {
     const int grid = int(std::min<int64_t>((rows + 7) / 8, 148 * 16));
-    launch_pdl(softmax_fwd_kernel, dim3(grid), dim3(256), size_t(0), ST, s, BFW(p), rows, n_valid, ld_in, ld_out);
+    launch_pdl(softmax_fwd_kernel, dim3(grid), dim3(256), size_t(0), ST, s, BFW(p), rows, n_valid, ld_in, ld_out, causal_period);
     return launch_checked(int(cudaGetLastError()), "softmax_fwd");
 }
 int t2v_softmax_bwd(const void* p, const float* dp, void* ds, int64_t rows, int32_t n_valid, int32_t ld_p, int32_t ld_dp, float scale,

@@ -430,12 +430,42 @@ def colsum_f32(x, out):
     native.check(native.lib().t2v_colsum_f32(_p(x), _p(out), x.shape[0], x.shape[1], _stream()))
 
 
-def softmax_fwd(s, n_valid, ld_out):
+def softmax_fwd(s, n_valid, ld_out, causal_period=0):
+    """Row softmax of fp32 scores [..., ld_in] -> bf16 probabilities [..., ld_out]; causal_period > 0: row r of the
+    flattened row index sees only columns <= r % causal_period (the CLIP text encoder's causal mask)."""
     _chk_f32(s)
     rows = s.numel() // s.shape[-1]
     p = torch.empty(s.shape[:-1] + (ld_out,), device=s.device, dtype=torch.bfloat16)
-    native.check(native.lib().t2v_softmax_fwd(_p(s), _p(p), rows, n_valid, s.shape[-1], ld_out, _stream()))
+    native.check(native.lib().t2v_softmax_fwd(_p(s), _p(p), rows, n_valid, s.shape[-1], ld_out, int(causal_period), _stream()))
     return p
+
+
+def gelu_bf16(x, quick=False):
+    _chk_bf16(x)
+    y = torch.empty_like(x)
+    native.check(native.lib().t2v_gelu_bf16(_p(x), _p(y), x.numel(), int(bool(quick)), _stream()))
+    return y
+
+
+def frames_u8_to_nhwc8(frames, out_hw):
+    """uint8 RGB frames [F, H0, W0, 3] -> bilinear resize + (x / 127.5 - 1) -> bf16 [F, h, w, 8] (VAE input layout)."""
+    assert frames.dtype == torch.uint8 and frames.is_cuda and frames.is_contiguous() and frames.shape[-1] == 3, (frames.dtype, frames.shape)
+    F, H0, W0, _ = frames.shape
+    h, w = out_hw
+    out = torch.empty((F, h, w, 8), device=frames.device, dtype=torch.bfloat16)
+    native.check(native.lib().t2v_frames_u8_to_nhwc8(_p(frames), _p(out), F, H0, W0, h, w, _stream()))
+    return out
+
+
+def embed_tokens(ids, tok_emb, pos_emb):
+    """ids int64 [B, L], tok_emb fp32 [vocab, C], pos_emb fp32 [>= L, C] -> bf16 [B*L, C] = tok_emb[ids] + pos_emb[l]."""
+    assert ids.dtype == torch.int64 and ids.is_cuda and ids.is_contiguous()
+    _chk_f32(tok_emb, pos_emb)
+    B, L = ids.shape
+    C = tok_emb.shape[1]
+    out = torch.empty((B * L, C), device=ids.device, dtype=torch.bfloat16)
+    native.check(native.lib().t2v_embed_tokens(_p(ids), _p(tok_emb), _p(pos_emb), _p(out), B * L, L, C, tok_emb.shape[0], _stream()))
+    return out
 
 
 def softmax_bwd(p, dp, n_valid, scale):

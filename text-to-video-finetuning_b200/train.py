@@ -8,9 +8,14 @@ noise + timestep sampling (:751-757), the fused add_noise -> UNet fwd+bwd -> MSE
 passes per video step like :814-834), ONE gradient all-reduce across ranks, clipping, AdamW, LR schedule, LoRA / UNet
 checkpoints.  One process per GPU (`torchrun --nproc-per-node N train.py --config ...`); no accelerate.
 
-Data: the hot path consumes latents.  Supported sources are the reference's latent cache (`cached_latent_dir` with
-`cached_{i}.pt` dicts written by `handle_cache_latents`, train.py:266-314) and `dataset_types: ['synthetic']`;
-raw-video datasets need decord and the VAE/text encoder (SURVEY section 8(f) 'next' rows) and raise a clear error.
+Data: `dataset_types` in ('json', 'single_video', 'image', 'folder') build the reference's dataset
+classes (utils/dataset.py: OpenCV decode -> ONE resize + normalise kernel on the GPU -> batched AutoencoderKL.encode);
+`cache_latents: True` writes / `cached_latent_dir` reads the reference's latent cache (`cached_{i}.pt`, train.py:266-314);
+`dataset_types: ['synthetic']` needs no files.  Prompts go through the frozen CLIP text encoder (text_encoder.py) with a
+per-prompt embedding cache; a batch that already carries `text_embeds` skips it.
+Checkpoints (8(f) row 4): LoRA in the cloneofsimo list format, the UNet in diffusers layout, and - when the pretrained folder
+is a full pipeline - the complete pipeline directory (`save_pipe`, train.py:395-449), plus a validation sample every
+`validation_steps` (sampling.py: DPM-Solver++ preview with the trained UNet in eval mode, train.py:908-958).
 """
 import argparse
 import itertools
@@ -120,6 +125,54 @@ class SyntheticLatents(torch.utils.data.Dataset):
     def __getitem__(self, i):
         g = torch.Generator().manual_seed(self.seed * 100003 + i)
         return {"pixel_values": torch.randn(self.shape, generator=g) * 0.18215, "text_embeds": torch.randn(self.tshape, generator=g)}
+
+
+def handle_cache_latents(should_cache, output_dir, train_dataloader, vae, device, cached_latent_dir=None):
+    """reference train.py:266-314: encode every item once and store it as cached_{i}.pt = {pixel_values: latents (4, F, h, w)
+    fp16, prompt_ids, text_prompt, dataset} (the reference's `batch[k] = v[0]` item format).  Returns the cache directory
+    (None when caching is off); an existing `cached_latent_dir` is used as is."""
+    if not should_cache:
+        return None
+    if cached_latent_dir is not None:
+        return os.path.abspath(cached_latent_dir)
+    from .utils.dataset import frames_to_latents
+    cache_save_dir = os.path.join(output_dir, "cached_latents")
+    os.makedirs(cache_save_dir, exist_ok=True)
+    for i, batch in enumerate(train_dataloader):
+        latents = frames_to_latents(batch, vae, device)
+        item = {"pixel_values": latents[0].to(torch.float16).cpu()}
+        for k, v in batch.items():
+            if k in ("frames_u8", "pixel_values", "pixel_hw"):
+                continue
+            v0 = v[0]
+            item[k] = v0.reshape(-1) if (torch.is_tensor(v0) and k == "prompt_ids") else v0
+        torch.save(item, os.path.join(cache_save_dir, f"cached_{i}.pt"))
+    return cache_save_dir
+
+
+class TextEmbedder:
+    """prompt ids -> encoder_hidden_states through the frozen text encoder (train.py:784-790), cached per distinct prompt:
+    a finetune run repeats a handful of prompts thousands of times."""
+
+    def __init__(self, text_encoder, device, max_entries=4096):
+        self.enc, self.device, self.cache, self.max = text_encoder, device, {}, max_entries
+
+    def __call__(self, prompt_ids):
+        ids = prompt_ids.reshape(-1, prompt_ids.shape[-1]).to(torch.int64).cpu()
+        out = []
+        for row in ids:
+            key = row.numpy().tobytes()
+            e = self.cache.get(key)
+            if e is None:
+                e = self.enc(row[None].to(self.device))[0][0]
+                if len(self.cache) < self.max:
+                    self.cache[key] = e
+            out.append(e)
+        return torch.stack(out)
+
+
+def _load_optional(cls, root, subfolder):
+    return cls.from_pretrained(root, subfolder=subfolder) if os.path.isfile(os.path.join(root, subfolder, "config.json")) else None
 
 
 def main(
@@ -248,6 +301,21 @@ def main(
     sched = torch.optim.lr_scheduler.LambdaLR(optimizer, _lr_lambda(lr_scheduler, lr_warmup_steps, max_train_steps))
 
     kinds = [dataset_types] if isinstance(dataset_types, str) else list(dataset_types)
+    # frozen side models, loaded only when the pretrained folder has them (a UNet-only folder trains from latents + embeddings)
+    vae = text_encoder = tokenizer = None
+    if dev.type == "cuda" or kwargs.get("load_side_models"):
+        from .text_encoder import CLIPTextModel
+        from .vae import AutoencoderKL
+        vae = _load_optional(AutoencoderKL, pretrained_model_path, "vae")
+        text_encoder = _load_optional(CLIPTextModel, pretrained_model_path, "text_encoder")
+        if vae is not None:
+            vae = vae.to(dev).eval()
+        if text_encoder is not None:
+            text_encoder = text_encoder.to(dev).eval()
+        if os.path.isdir(os.path.join(pretrained_model_path, "tokenizer")):
+            from transformers import CLIPTokenizer
+            tokenizer = CLIPTokenizer.from_pretrained(pretrained_model_path, subfolder="tokenizer")
+    embed_text = TextEmbedder(text_encoder, dev) if text_encoder is not None else None
     if cached_latent_dir:
         dataset = CachedLatents(cached_latent_dir)
     elif "synthetic" in kinds:
@@ -256,8 +324,25 @@ def main(
                                    hw=(td.get("height", 256) // 8, td.get("width", 256) // 8),
                                    text_dim=unet.config.cross_attention_dim)
     else:
-        raise NotImplementedError(f"dataset_types={kinds}: raw-video datasets need decord + VAE/text encoders (SURVEY 8(f)); "
-                                  "use cached_latent_dir or dataset_types: ['synthetic']")
+        from .utils.dataset import extend_datasets, get_train_dataset
+        if vae is None:
+            raise FileNotFoundError(f"dataset_types={kinds} need the VAE of the pipeline: {pretrained_model_path}/vae is missing")
+        if tokenizer is None or text_encoder is None:
+            raise FileNotFoundError(f"dataset_types={kinds} need {pretrained_model_path}/tokenizer and /text_encoder for the prompts")
+        parts = get_train_dataset(kinds, train_data, tokenizer)
+        for extra in extra_train_data or []:
+            parts += get_train_dataset(kinds, extra, tokenizer)
+        extend_datasets(parts, ["train_data", "frames", "image_dir", "video_files"], extend=extend_dataset)
+        parts = [d for d in parts if len(d) > 0]
+        if not parts:
+            raise FileNotFoundError(f"dataset_types={kinds}: no training items found under {train_data}")
+        dataset = torch.utils.data.ConcatDataset(parts)
+        if cache_latents:   # encode once, then train from the cache (reference handle_cache_latents)
+            if rank == 0:
+                handle_cache_latents(True, output_dir, torch.utils.data.DataLoader(dataset, batch_size=1, shuffle=False), vae, dev)
+            if world > 1:
+                dist.barrier()
+            dataset = CachedLatents(os.path.join(output_dir, "cached_latents"))
     sampler = torch.utils.data.distributed.DistributedSampler(dataset, world, rank, shuffle=shuffle) if world > 1 else None
     loader = torch.utils.data.DataLoader(dataset, batch_size=train_batch_size, shuffle=shuffle and sampler is None, sampler=sampler)
 
@@ -269,10 +354,19 @@ def main(
             sampler.set_epoch(epoch)   # a new shuffle every epoch
         epoch += 1
         for batch in loader:
-            latents = batch["pixel_values"].to(dev, torch.float32)
-            if "text_embeds" not in batch:
-                raise NotImplementedError("batch has no 'text_embeds': the frozen text encoder is a SURVEY 8(f) 'next' row")
-            text = batch["text_embeds"].to(dev, torch.float32)
+            if "frames_u8" in batch or (batch["pixel_values"].dim() == 5 and batch["pixel_values"].shape[2] == 3
+                                        and batch["pixel_values"].shape[1] != 4):
+                from .utils.dataset import frames_to_latents
+                latents = frames_to_latents(batch, vae, dev)        # raw clip -> resize/normalise kernel -> batched VAE encode
+            else:
+                latents = batch["pixel_values"].to(dev, torch.float32)
+            if "text_embeds" in batch:
+                text = batch["text_embeds"].to(dev, torch.float32)
+            elif embed_text is not None and "prompt_ids" in batch:
+                text = embed_text(batch["prompt_ids"])                # frozen CLIP text encoder, cached per prompt
+            else:
+                raise FileNotFoundError("batch has neither 'text_embeds' nor a text encoder to turn 'prompt_ids' into them "
+                                        f"({pretrained_model_path}/text_encoder is missing)")
             noise = sample_noise(latents, offset_noise_strength, use_offset_noise and not rescale_schedule)
             timesteps = torch.randint(0, abar.shape[0], (latents.shape[0],), device=dev, dtype=torch.int64)
             if latents.shape[2] <= 1:
@@ -296,18 +390,53 @@ def main(
             if rank == 0 and (global_step % 10 == 0 or global_step == 1):
                 print(f"step {global_step}/{max_train_steps} loss {loss.item():.5f} ({(time.time() - t0) / global_step:.3f} s/step)")
             if rank == 0 and global_step % checkpointing_steps == 0:
-                save_checkpoint(unet, lora_manager, output_dir, global_step, use_unet_lora, save_pretrained_model)
+                save_checkpoint(unet, lora_manager, output_dir, global_step, use_unet_lora, save_pretrained_model,
+                                pretrained_model_path=pretrained_model_path)
+            if rank == 0 and validation_data and validation_steps and global_step % validation_steps == 0 and vae is not None \
+                    and text_encoder is not None and tokenizer is not None and getattr(vae, "decoder", None) is not None:
+                from .sampling import validation_sample
+                validation_sample(unet, vae, text_encoder, tokenizer, validation_data, os.path.join(output_dir, "samples"), global_step,
+                                  batch.get("text_prompt", [""])[0] if isinstance(batch.get("text_prompt"), (list, tuple)) else "", dev)
             if global_step >= max_train_steps:
                 break
     if world > 1:
         dist.barrier()
     if rank == 0:
-        save_checkpoint(unet, lora_manager, output_dir, global_step, use_unet_lora, save_pretrained_model, final=True)
+        save_checkpoint(unet, lora_manager, output_dir, global_step, use_unet_lora, save_pretrained_model, final=True,
+                        pretrained_model_path=pretrained_model_path)
     return {"steps": global_step, "step_times": step_times, "stepper": stepper, "optimizer": optimizer}
 
 
-def save_checkpoint(unet, lora_manager, output_dir, step, use_unet_lora, save_pretrained_model, final=False):
-    """LoRA in the cloneofsimo list format (`lora/<step>_unet.pt`), UNet in diffusers layout (`unet/`)."""
+PIPELINE_PARTS = ("vae", "text_encoder", "tokenizer", "scheduler")
+
+
+def save_pipe(pretrained_model_path, unet, path):
+    """reference save_pipe (train.py:395-449): a complete TextToVideoSDPipeline directory - the trained UNet in diffusers
+    layout plus the frozen parts and model_index.json of the pretrained pipeline, so `from_pretrained(path)` of a diffusers
+    pipeline (or train.main again) can load it.  A UNet-only pretrained folder yields a UNet-only checkpoint."""
+    import shutil
+    os.makedirs(path, exist_ok=True)
+    unet.save_pretrained(os.path.join(path, "unet"))
+    copied = []
+    for part in PIPELINE_PARTS:
+        src = os.path.join(pretrained_model_path, part)
+        if os.path.isdir(src):
+            shutil.copytree(src, os.path.join(path, part), dirs_exist_ok=True)
+            copied.append(part)
+    index = os.path.join(pretrained_model_path, "model_index.json")
+    if os.path.isfile(index):
+        shutil.copyfile(index, os.path.join(path, "model_index.json"))
+    elif copied:
+        import json
+        with open(os.path.join(path, "model_index.json"), "w") as f:
+            json.dump({"_class_name": "TextToVideoSDPipeline", "unet": ["diffusers", "UNet3DConditionModel"],
+                       "vae": ["diffusers", "AutoencoderKL"], "text_encoder": ["transformers", "CLIPTextModel"],
+                       "tokenizer": ["transformers", "CLIPTokenizer"], "scheduler": ["diffusers", "DDIMScheduler"]}, f, indent=2)
+    return copied
+
+
+def save_checkpoint(unet, lora_manager, output_dir, step, use_unet_lora, save_pretrained_model, final=False, pretrained_model_path=None):
+    """LoRA in the cloneofsimo list format (`lora/<step>_unet.pt`) and, with save_pretrained_model, the pipeline directory."""
     path = output_dir if final else os.path.join(output_dir, f"checkpoint-{step}")
     os.makedirs(path, exist_ok=True)
     if use_unet_lora:   # the reference saves the LoRA files and (save_pretrained_model) the pipeline: train.py:908-958
@@ -315,7 +444,10 @@ def save_checkpoint(unet, lora_manager, output_dir, step, use_unet_lora, save_pr
         os.makedirs(os.path.join(path, "lora"), exist_ok=True)
         save_lora_weight(unet, os.path.join(path, "lora", f"{step}_unet.pt"), lora_manager.unet_replace_modules)
     if save_pretrained_model:
-        unet.save_pretrained(os.path.join(path, "unet"))
+        if pretrained_model_path is not None:
+            save_pipe(pretrained_model_path, unet, path)
+        else:
+            unet.save_pretrained(os.path.join(path, "unet"))
 
 
 def load_config(path):

@@ -137,7 +137,11 @@ class AutoencoderKL(ModelMixin, ConfigMixin):
     def encode_moments(self, x):
         """x (N, 3, H, W) in [-1, 1] -> moments [N, H/8, W/8, 8] bf16 channels-last (mean | logvar)."""
         N, C, H, W = x.shape
-        xin = prims.latents_to_nhwc8(x.float().contiguous().view(N, C, 1, H, W))
+        return self.encode_moments_nhwc8(prims.latents_to_nhwc8(x.float().contiguous().view(N, C, 1, H, W)))
+
+    @torch.no_grad()
+    def encode_moments_nhwc8(self, xin):
+        """xin bf16 [N, H, W, 8] channels-last in [-1, 1] (what prims.frames_u8_to_nhwc8 produces) -> moments [N, H/8, W/8, 8]."""
         return run_conv(self.quant_conv, self.encoder(xin), pads=(0, 0, 0, 0))
 
     def encode(self, x, return_dict=True):
