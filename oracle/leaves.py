@@ -177,6 +177,25 @@ def vae_encode_moments(p, x, block_out_channels=(128, 256, 512, 512), layers_per
     return F.conv2d(h, p[pre + "quant_conv.weight"], p[pre + "quant_conv.bias"])
 
 
+def vae_decode(p, z, block_out_channels=(128, 256, 512, 512), layers_per_block=2, groups=32, pre=""):
+    """AutoencoderKL.decode: post_quant_conv + SD-VAE decoder (mid block, 4 up blocks of layers_per_block + 1 resnets, nearest
+    x2 upsample + conv between them).  z: unscaled latents (N, 4, h, w).  Used by the validation preview (train.py:908-958)."""
+    d = pre + "decoder."
+    rev = tuple(reversed(block_out_channels))
+    h = F.conv2d(z, p[pre + "post_quant_conv.weight"], p[pre + "post_quant_conv.bias"])
+    h = F.conv2d(h, p[d + "conv_in.weight"], p[d + "conv_in.bias"], padding=1)
+    h = resnet_block2d(p, d + "mid_block.resnets.0.", h, None, groups, 1e-6)
+    h = vae_attention(p, d + "mid_block.attentions.0.", h, groups)
+    h = resnet_block2d(p, d + "mid_block.resnets.1.", h, None, groups, 1e-6)
+    for i in range(len(rev)):
+        for j in range(layers_per_block + 1):
+            h = resnet_block2d(p, f"{d}up_blocks.{i}.resnets.{j}.", h, None, groups, 1e-6)
+        if i != len(rev) - 1:
+            h = upsample2d(p, f"{d}up_blocks.{i}.upsamplers.0.", h, None)
+    h = F.group_norm(h, groups, p[d + "conv_norm_out.weight"], p[d + "conv_norm_out.bias"], 1e-6)
+    return F.conv2d(F.silu(h), p[d + "conv_out.weight"], p[d + "conv_out.bias"], padding=1)
+
+
 def diagonal_gaussian_sample(moments, eps_noise):
     """DiagonalGaussianDistribution.sample(): mean + exp(0.5 * clamp(logvar, -30, 20)) * eps."""
     mean, logvar = moments.chunk(2, dim=1)

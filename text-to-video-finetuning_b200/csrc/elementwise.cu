@@ -138,7 +138,7 @@ __global__ void gelu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* 
         float v[8];
         unpack8e(__ldg(reinterpret_cast<const uint4*>(x) + i), v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = quick ? v[j] / (1.f + __expf(-1.702f * v[j])) : v[j] * gelu_erf(v[j]);
+        for (int j = 0; j < 8; ++j) v[j] = quick ? v[j] / (1.f + __expf(-1.702f * v[j])) : gelu_erf(v[j]);
         reinterpret_cast<uint4*>(y)[i] = pack8e(v);
     }
 }
