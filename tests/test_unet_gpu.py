@@ -74,6 +74,18 @@ def test_non_power_of_two_and_checkpointing():
     _check(*_case(SMALL, 1, 3, (24, 40), ckpt=True))
 
 
+def test_cfg3_shape_24_frames_ragged_map():
+    """configs[2] geometry at reduced width: 24 frames of a 40x72-like (non-square, not a multiple of 16) latent map - the
+    epilogue-statistics fallback, ragged pixel boxes and the F = 24 temporal kernels (attn_small L = 24)."""
+    _check(*_case(SMALL, 1, 24, (10, 18)))
+
+
+def test_cfg4_shape_32_frames_with_gradient_checkpointing():
+    """configs[3] geometry at reduced width: 32 frames (attn_small L = 32, its maximum), gradient checkpointing on, so the
+    backward runs on recomputed activations (and recomputed epilogue statistics)."""
+    _check(*_case(SMALL, 1, 32, (16, 16), ckpt=True))
+
+
 def test_single_frame():
     _check(*_case(SMALL, 2, 1, (16, 16)), skip_temporal=True)
 

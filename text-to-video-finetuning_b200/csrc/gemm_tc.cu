@@ -97,6 +97,22 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
     // swizzled byte offset of logical 16-byte chunk j of row r in a dense [32][n] chunk array
     auto phys = [](int r, int j, int n) { return (r * n + (j ^ (((r * n) >> 3) & (n - 1)))) * 16; };
     const int sr = lane / CPR, sj = lane % CPR;  // (row-in-group, chunk) this lane moves in the coalesced phases
+    // tile-invariant shared-memory addresses of the staging tile (hoisted: the fast path below is straight-line code)
+    uint8_t* w_own[CPR];     // this lane's own row, 16-byte chunk j                     (write after the math)
+    uint8_t* r_mov[CPR];     // the (row, chunk) this lane moves in the coalesced store   (read)
+    uint8_t* w_res[4];       // residual staging: row (lane / 4) + 8 i, chunk lane % 4   (write, bf16 rows of 64 B)
+    uint8_t* r_res[4];       // residual staging: own row, chunk j                       (read)
+#pragma unroll
+    for (int j = 0; j < CPR; ++j) {
+        w_own[j] = stg + phys(static_cast<int>(lane), j, CPR);
+        r_mov[j] = stg + phys(sr + RPI * j, sj, CPR);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        w_res[j] = stg + phys(static_cast<int>(lane >> 2) + 8 * j, static_cast<int>(lane & 3), 4);
+        r_res[j] = stg + phys(static_cast<int>(lane), j, 4);
+    }
+    const bool alpha_one = p.alpha == 1.0f;
     uint32_t it = 0;
     for (int32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         TileVars tv;
@@ -120,6 +136,8 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
             ok_s |= (__shfl_sync(0xffffffffu, row_ok ? 1u : 0u, r) & 1u) << i;
         }
         const int32_t col0 = tv.t[0] * p.block_n;
+        // every row of this warp inside the output: the common case runs without per-row predicates
+        const bool all_rows = vec && __all_sync(0xffffffffu, row_ok);
         // GroupNorm statistics: frame of this lane's segment (taken from the segment's first row, which is in bounds
         // whenever any row of the segment is)
         int64_t st_off = 0;
@@ -140,6 +158,102 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
             const int32_t col = col0 + ch * 32;
             const int32_t cvalid = min(32, min(p.block_n - ch * 32, p.ncols - col));  // valid columns of this chunk
             __syncwarp();
+            if (all_rows && cvalid == 32) {
+                // ---- fast path: a full 32 x 32 chunk, every row in bounds - straight-line code, no per-row predicates
+                if (has_bias) sbias[lane] = __ldg(p.bias + col + lane);
+                if (has_res) {   // residual: coalesced global -> staging
+                    const __nv_bfloat16* rb = static_cast<const __nv_bfloat16*>(p.residual) + col + (lane & 3) * 8;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int64_t off_r = __shfl_sync(0xffffffffu, off, (lane >> 2) + 8 * i);
+                        *reinterpret_cast<uint4*>(w_res[i]) = __ldg(reinterpret_cast<const uint4*>(rb + off_r));
+                    }
+                }
+                tmem_ld_wait();
+                float v[32];
+                if (alpha_one) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * p.alpha;
+                }
+                if (ch + 1 < c_end) tmem_ld32(taddr + (ch + 1) * 32, acc);
+                __syncwarp();
+                if (has_bias) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = *reinterpret_cast<const float4*>(sbias + 4 * j);  // shared-memory broadcast
+                        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                    }
+                }
+                if (has_rb) {
+                    const float4* b4 = reinterpret_cast<const float4*>(p.rowbias + (gn / p.rb_div) * p.rb_ld + col);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = __ldg(b4 + j);
+                        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                    }
+                }
+                if (has_res) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 q = *reinterpret_cast<const uint4*>(r_res[j]);
+                        v[8 * j + 0] += bf16_lo(q.x); v[8 * j + 1] += bf16_hi(q.x);
+                        v[8 * j + 2] += bf16_lo(q.y); v[8 * j + 3] += bf16_hi(q.y);
+                        v[8 * j + 4] += bf16_lo(q.z); v[8 * j + 5] += bf16_hi(q.z);
+                        v[8 * j + 6] += bf16_lo(q.w); v[8 * j + 7] += bf16_hi(q.w);
+                    }
+                    __syncwarp();
+                }
+                if (ESZ == 2) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 q;
+                        q.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+                        q.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+                        q.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+                        q.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+                        *reinterpret_cast<uint4*>(w_own[j]) = q;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < CPR; ++j)
+                        *reinterpret_cast<float4*>(w_own[j]) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                __syncwarp();
+                if (ESZ == 2 && has_stats) {   // GroupNorm statistics of the staged bf16 tile (see the general path below)
+                    const uint32_t half = lane >> 4, cw = lane & 15u;
+                    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int r = half ? 16 + ((i + 1) & 15) : i;
+                        const uint32_t w = *reinterpret_cast<const uint32_t*>(stg + phys(r, int(cw >> 2), 4) + (cw & 3u) * 4u);
+                        const float lo = bf16_lo(w), hi = bf16_hi(w);
+                        s0 += lo; q0 += lo * lo;
+                        s1 += hi; q1 += hi * hi;
+                    }
+                    if (p.st_seg == 32) {
+                        s0 += __shfl_xor_sync(0xffffffffu, s0, 16); q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+                    }
+                    if (p.st_seg == 16 || half == 0) red_add_f32x4(p.stats + (st_off + col + 2 * cw) * 2, s0, q0, s1, q1);
+                }
+                // staging -> global: 16 bytes per lane, whole row segments
+                char* ob = static_cast<char*>(p.out) + (static_cast<int64_t>(col) + sj * EPC) * ESZ;
+#pragma unroll
+                for (int i = 0; i < CPR; ++i) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(r_mov[i]);
+                    char* o = ob + off_s[i] * ESZ;
+                    if (ESZ == 2 || p.out_mode == OUT_F32) {
+                        *reinterpret_cast<uint4*>(o) = q;
+                    } else {
+                        red_add_f32x4(reinterpret_cast<float*>(o), __uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z),
+                                      __uint_as_float(q.w));
+                    }
+                }
+                continue;
+            }
             float bval = 0.f;
             if (has_bias && static_cast<int32_t>(lane) < cvalid) bval = __ldg(p.bias + col + lane);
             if (vec && has_res && cvalid > 0) {         // residual: coalesced global -> staging (bf16, 4 chunks per row)

@@ -348,7 +348,7 @@ def main(
 
     global_step, micro, epoch = 0, 0, 0
     t0 = time.time()
-    step_times = []
+    step_times, t_iter = [], time.perf_counter()
     while global_step < max_train_steps:
         if sampler is not None:
             sampler.set_epoch(epoch)   # a new shuffle every epoch
@@ -371,7 +371,6 @@ def main(
             timesteps = torch.randint(0, abar.shape[0], (latents.shape[0],), device=dev, dtype=torch.int64)
             if latents.shape[2] <= 1:
                 stepper.passes = 1  # single-frame data breaks out after the first pass (train.py:832)
-            t_step = time.perf_counter()
             loss = stepper(latents, noise, timesteps, text)   # fused: on a window boundary this includes clip + AdamW
             micro += 1
             if micro % gradient_accumulation_steps:
@@ -384,9 +383,11 @@ def main(
                 optimizer.step()
             sched.step()
             global_step += 1
-            if kwargs.get("_time_steps"):   # test hook: synchronous per-step wall time (tests/test_train_loop.py)
+            if kwargs.get("_time_steps"):   # test hook: synchronous wall time of the WHOLE iteration (data, noise, step, optimizer)
                 torch.cuda.synchronize()
-                step_times.append(time.perf_counter() - t_step)
+                now = time.perf_counter()
+                step_times.append(now - t_iter)
+                t_iter = now
             if rank == 0 and (global_step % 10 == 0 or global_step == 1):
                 print(f"step {global_step}/{max_train_steps} loss {loss.item():.5f} ({(time.time() - t0) / global_step:.3f} s/step)")
             if rank == 0 and global_step % checkpointing_steps == 0:
