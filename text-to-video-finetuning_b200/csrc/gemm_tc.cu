@@ -98,19 +98,20 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
     auto phys = [](int r, int j, int n) { return (r * n + (j ^ (((r * n) >> 3) & (n - 1)))) * 16; };
     const int sr = lane / CPR, sj = lane % CPR;  // (row-in-group, chunk) this lane moves in the coalesced phases
     // tile-invariant shared-memory addresses of the staging tile (hoisted: the fast path below is straight-line code)
-    uint8_t* w_own[CPR];     // this lane's own row, 16-byte chunk j                     (write after the math)
-    uint8_t* r_mov[CPR];     // the (row, chunk) this lane moves in the coalesced store   (read)
-    uint8_t* w_res[4];       // residual staging: row (lane / 4) + 8 i, chunk lane % 4   (write, bf16 rows of 64 B)
-    uint8_t* r_res[4];       // residual staging: own row, chunk j                       (read)
+    const uint32_t stg_s = smem_u32(stg);
+    uint32_t w_own[CPR];     // this lane's own row, 16-byte chunk j                     (write after the math)
+    uint32_t r_mov[CPR];     // the (row, chunk) this lane moves in the coalesced store   (read)
+    uint32_t w_res[4];       // residual staging: row (lane / 4) + 8 i, chunk lane % 4   (write, bf16 rows of 64 B)
+    uint32_t r_res[4];       // residual staging: own row, chunk j                       (read)
 #pragma unroll
     for (int j = 0; j < CPR; ++j) {
-        w_own[j] = stg + phys(static_cast<int>(lane), j, CPR);
-        r_mov[j] = stg + phys(sr + RPI * j, sj, CPR);
+        w_own[j] = stg_s + phys(static_cast<int>(lane), j, CPR);
+        r_mov[j] = stg_s + phys(sr + RPI * j, sj, CPR);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        w_res[j] = stg + phys(static_cast<int>(lane >> 2) + 8 * j, static_cast<int>(lane & 3), 4);
-        r_res[j] = stg + phys(static_cast<int>(lane), j, 4);
+        w_res[j] = stg_s + phys(static_cast<int>(lane >> 2) + 8 * j, static_cast<int>(lane & 3), 4);
+        r_res[j] = stg_s + phys(static_cast<int>(lane), j, 4);
     }
     const bool alpha_one = p.alpha == 1.0f;
     uint32_t it = 0;
@@ -147,6 +148,38 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
             st_off = int64_t(__shfl_sync(0xffffffffu, fr, lane & ~uint32_t(p.st_seg - 1))) * p.st_ld;
             okmask = __ballot_sync(0xffffffffu, row_ok);
         }
+        // ---- software pipeline of the epilogue's global loads.  Per-column additive terms (bias, and the time-embedding row
+        // when every row of this warp takes the same one) are fetched two chunks ahead, the residual tile one chunk ahead;
+        // the first of them are issued BEFORE the wait for the accumulator, so their latency hides behind the main loop.
+        const int32_t rb_row = has_rb ? gn / p.rb_div : 0;
+        const bool rb_uniform = has_rb && vec && __all_sync(0xffffffffu, !row_ok || rb_row == __shfl_sync(0xffffffffu, rb_row, 0));
+        const float* rb_base = has_rb ? p.rowbias + static_cast<int64_t>(__shfl_sync(0xffffffffu, rb_row, 0)) * p.rb_ld : nullptr;
+        auto load_colterm = [&](int ch) {
+            const int32_t c = col0 + ch * 32 + static_cast<int32_t>(lane);
+            float b = 0.f;
+            if (static_cast<int32_t>(lane) < min(32, min(p.block_n - ch * 32, p.ncols - (col0 + ch * 32)))) {
+                if (has_bias) b = __ldg(p.bias + c);
+                if (rb_uniform) b += __ldg(rb_base + c);
+            }
+            return b;
+        };
+        const bool res_pref = all_rows && has_res;
+        const __nv_bfloat16* res_lane = static_cast<const __nv_bfloat16*>(p.residual) + (lane & 3) * 8;
+        int64_t off_q[4];   // residual rows this lane fetches: (lane / 4) + 8 i
+#pragma unroll
+        for (int i = 0; i < 4; ++i) off_q[i] = __shfl_sync(0xffffffffu, off, (lane >> 2) + 8 * i);
+        auto load_res = [&](int ch, uint4 (&q)[4]) {
+            const int32_t c = col0 + ch * 32;
+            if (min(p.block_n - ch * 32, p.ncols - c) >= 32) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) q[i] = __ldg(reinterpret_cast<const uint4*>(res_lane + off_q[i] + c));
+            }
+        };
+        float bq0 = 0.f, bq1 = 0.f;
+        uint4 rq[4] = {};
+        if (c_begin < c_end) bq0 = load_colterm(c_begin);
+        if (c_begin + 1 < c_end) bq1 = load_colterm(c_begin + 1);
+        if (res_pref && c_begin < c_end) load_res(c_begin, rq);
         const uint32_t as = p.nacc == 2 ? (it & 1u) : 0u;
         const uint32_t aphase = p.nacc == 2 ? ((it >> 1) & 1u) : (it & 1u);
         mbar_wait(&acc_full[as], aphase);
@@ -158,16 +191,20 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
             const int32_t col = col0 + ch * 32;
             const int32_t cvalid = min(32, min(p.block_n - ch * 32, p.ncols - col));  // valid columns of this chunk
             __syncwarp();
+            const float bcur = bq0;          // this chunk's per-column term; keep the pipeline two chunks deep
+            bq0 = bq1;
+            if (ch + 2 < c_end) bq1 = load_colterm(ch + 2);
+            uint4 rcur[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rcur[i] = rq[i];
+            if (res_pref && ch + 1 < c_end) load_res(ch + 1, rq);
+            const bool colterm = has_bias || rb_uniform;
             if (all_rows && cvalid == 32) {
                 // ---- fast path: a full 32 x 32 chunk, every row in bounds - straight-line code, no per-row predicates
-                if (has_bias) sbias[lane] = __ldg(p.bias + col + lane);
-                if (has_res) {   // residual: coalesced global -> staging
-                    const __nv_bfloat16* rb = static_cast<const __nv_bfloat16*>(p.residual) + col + (lane & 3) * 8;
+                if (colterm) sbias[lane] = bcur;
+                if (has_res) {   // residual (prefetched): registers -> staging
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int64_t off_r = __shfl_sync(0xffffffffu, off, (lane >> 2) + 8 * i);
-                        *reinterpret_cast<uint4*>(w_res[i]) = __ldg(reinterpret_cast<const uint4*>(rb + off_r));
-                    }
+                    for (int i = 0; i < 4; ++i) sts128(w_res[i], rcur[i]);
                 }
                 tmem_ld_wait();
                 float v[32];
@@ -180,14 +217,14 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
                 }
                 if (ch + 1 < c_end) tmem_ld32(taddr + (ch + 1) * 32, acc);
                 __syncwarp();
-                if (has_bias) {
+                if (colterm) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float4 b = *reinterpret_cast<const float4*>(sbias + 4 * j);  // shared-memory broadcast
                         v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
                     }
                 }
-                if (has_rb) {
+                if (has_rb && !rb_uniform) {
                     const float4* b4 = reinterpret_cast<const float4*>(p.rowbias + (gn / p.rb_div) * p.rb_ld + col);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -198,7 +235,7 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
                 if (has_res) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const uint4 q = *reinterpret_cast<const uint4*>(r_res[j]);
+                        const uint4 q = lds128(r_res[j]);
                         v[8 * j + 0] += bf16_lo(q.x); v[8 * j + 1] += bf16_hi(q.x);
                         v[8 * j + 2] += bf16_lo(q.y); v[8 * j + 3] += bf16_hi(q.y);
                         v[8 * j + 4] += bf16_lo(q.z); v[8 * j + 5] += bf16_hi(q.z);
@@ -214,12 +251,13 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
                         q.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
                         q.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
                         q.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-                        *reinterpret_cast<uint4*>(w_own[j]) = q;
+                        sts128(w_own[j], q);
                     }
                 } else {
 #pragma unroll
                     for (int j = 0; j < CPR; ++j)
-                        *reinterpret_cast<float4*>(w_own[j]) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        sts128(w_own[j], make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                                                    __float_as_uint(v[4 * j + 3])));
                 }
                 __syncwarp();
                 if (ESZ == 2 && has_stats) {   // GroupNorm statistics of the staged bf16 tile (see the general path below)
@@ -228,7 +266,7 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int r = half ? 16 + ((i + 1) & 15) : i;
-                        const uint32_t w = *reinterpret_cast<const uint32_t*>(stg + phys(r, int(cw >> 2), 4) + (cw & 3u) * 4u);
+                        const uint32_t w = lds32(stg_s + phys(r, int(cw >> 2), 4) + (cw & 3u) * 4u);
                         const float lo = bf16_lo(w), hi = bf16_hi(w);
                         s0 += lo; q0 += lo * lo;
                         s1 += hi; q1 += hi * hi;
@@ -243,7 +281,7 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
                 char* ob = static_cast<char*>(p.out) + (static_cast<int64_t>(col) + sj * EPC) * ESZ;
 #pragma unroll
                 for (int i = 0; i < CPR; ++i) {
-                    const uint4 q = *reinterpret_cast<const uint4*>(r_mov[i]);
+                    const uint4 q = lds128(r_mov[i]);
                     char* o = ob + off_s[i] * ESZ;
                     if (ESZ == 2 || p.out_mode == OUT_F32) {
                         *reinterpret_cast<uint4*>(o) = q;
@@ -254,8 +292,7 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
                 }
                 continue;
             }
-            float bval = 0.f;
-            if (has_bias && static_cast<int32_t>(lane) < cvalid) bval = __ldg(p.bias + col + lane);
+            const float bval = bcur;   // bias (+ the warp-uniform time-embedding row) of this chunk, fetched two chunks ago
             if (vec && has_res && cvalid > 0) {         // residual: coalesced global -> staging (bf16, 4 chunks per row)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -277,14 +314,14 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
             __syncwarp();
             if (cvalid <= 0) continue;
             if (vec) {
-                if (has_bias) {
+                if (colterm) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float4 b = *reinterpret_cast<const float4*>(sbias + 4 * j);  // shared-memory broadcast
                         v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
                     }
                 }
-                if (has_rb && row_ok) {
+                if (has_rb && !rb_uniform && row_ok) {
                     const float4* b4 = reinterpret_cast<const float4*>(p.rowbias + (gn / p.rb_div) * p.rb_ld + col);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
