@@ -151,9 +151,12 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
         // ---- software pipeline of the epilogue's global loads.  Per-column additive terms (bias, and the time-embedding row
         // when every row of this warp takes the same one) are fetched two chunks ahead, the residual tile one chunk ahead;
         // the first of them are issued BEFORE the wait for the accumulator, so their latency hides behind the main loop.
+        // (every lane takes part in the shuffle: it must not sit behind a short-circuit that depends on row_ok)
         const int32_t rb_row = has_rb ? gn / p.rb_div : 0;
-        const bool rb_uniform = has_rb && vec && __all_sync(0xffffffffu, !row_ok || rb_row == __shfl_sync(0xffffffffu, rb_row, 0));
-        const float* rb_base = has_rb ? p.rowbias + static_cast<int64_t>(__shfl_sync(0xffffffffu, rb_row, 0)) * p.rb_ld : nullptr;
+        const int32_t rb_first = __shfl_sync(0xffffffffu, rb_row, 0);
+        const bool rb_same = !row_ok || rb_row == rb_first;
+        const bool rb_uniform = has_rb && vec && __all_sync(0xffffffffu, rb_same);
+        const float* rb_base = has_rb ? p.rowbias + static_cast<int64_t>(rb_first) * p.rb_ld : nullptr;
         auto load_colterm = [&](int ch) {
             const int32_t c = col0 + ch * 32 + static_cast<int32_t>(lane);
             float b = 0.f;
