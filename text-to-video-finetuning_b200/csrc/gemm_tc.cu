@@ -152,10 +152,13 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
         // when every row of this warp takes the same one) are fetched two chunks ahead, the residual tile one chunk ahead;
         // the first of them are issued BEFORE the wait for the accumulator, so their latency hides behind the main loop.
         // (every lane takes part in the shuffle: it must not sit behind a short-circuit that depends on row_ok)
+        // The row is taken from the warp's first IN-BOUNDS lane: an out-of-bounds lane (frames beyond N in the last tile) would
+        // name a row past the end of the time-embedding matrix.  A warp without any valid row folds nothing.
         const int32_t rb_row = has_rb ? gn / p.rb_div : 0;
-        const int32_t rb_first = __shfl_sync(0xffffffffu, rb_row, 0);
+        const uint32_t ok_lanes = __ballot_sync(0xffffffffu, row_ok);
+        const int32_t rb_first = __shfl_sync(0xffffffffu, rb_row, ok_lanes ? __ffs(ok_lanes) - 1 : 0);
         const bool rb_same = !row_ok || rb_row == rb_first;
-        const bool rb_uniform = has_rb && vec && __all_sync(0xffffffffu, rb_same);
+        const bool rb_uniform = has_rb && vec && ok_lanes != 0u && __all_sync(0xffffffffu, rb_same);
         const float* rb_base = has_rb ? p.rowbias + static_cast<int64_t>(rb_first) * p.rb_ld : nullptr;
         auto load_colterm = [&](int ch) {
             const int32_t c = col0 + ch * 32 + static_cast<int32_t>(lane);

@@ -15,6 +15,7 @@ from t2v_b200 import prims  # noqa: E402
 kind = sys.argv[1]
 N, H, W, Ci, Co, KH, KW = (int(v) for v in sys.argv[2:9])
 reps = int(sys.argv[9]) if len(sys.argv) > 9 else 5
+with_stats = "stats" in sys.argv      # forward only: also produce the per-frame GroupNorm statistics in the epilogue
 pads = ((KH - 1) // 2, (KH - 1) // 2, (KW - 1) // 2, (KW - 1) // 2)
 dev = "cuda"
 x = torch.randn(N, H, W, Ci, device=dev).bfloat16()
@@ -27,7 +28,8 @@ for i in range(reps + 2):
     if i == 2:
         e0.record()
     if kind == "fwd":
-        prims.conv_fwd(x, w, bias, None, None, 1, pads)
+        st = prims.stats_alloc(N, Co, dev) if with_stats else None
+        prims.conv_fwd(x, w, bias, None, None, 1, pads, stats=st, stats_rows=H * W if with_stats else 0)
     elif kind == "dgrad":
         prims.conv_dgrad(dy, w, (H, W), 1, pads)
     else:
