@@ -3,9 +3,9 @@
 
 Tolerances (stated, not tuned): north_star asks 1e-3 relative on loss and gradients.
   * scalar loss:       <= 1e-3 relative                                  (asserted)
-  * global grad-norm:  <= 5e-3 relative.  bf16 storage of activations and output gradients bounds this from below: SURVEY
+  * global grad-norm:  <= 3e-3 relative.  bf16 storage of activations and output gradients bounds this from below: SURVEY
     8(c) measured torch's OWN bf16-autocast path against its fp32 path at 1.3e-3 (F = 8), i.e. the reference's GPU
-    configuration does not meet 1e-3 on this quantity either; 5e-3 is < 4x that floor and is asserted.
+    configuration does not meet 1e-3 on this quantity either; 3e-3 is ~2x that floor and is asserted (measured 3e-4 .. 1.4e-3).
   * prediction:        rel-L2 <= 4e-2, cosine >= 0.999 (torch autocast 1.4e-2)
 The oracle pass takes about a minute on the GPU box's host cores."""
 import os
@@ -59,6 +59,6 @@ def test_full_size_cfg2_loss_and_gradnorm_vs_oracle():
     print(f"full-size parity: loss {float(loss):.6f} vs {float(loss_r):.6f} (rel {loss_rel:.2e}); grad-norm {gn:.5f} vs {gn_r:.5f} "
           f"(rel {gn_rel:.2e}); pred rel-L2 {err:.2e} cos {cos:.6f}; grad cosines {min(coss.values()):.4f}..{max(coss.values()):.4f}")
     assert loss_rel <= 1e-3, loss_rel
-    assert gn_rel <= 5e-3, gn_rel
+    assert gn_rel <= 3e-3, gn_rel
     assert err <= 4e-2 and cos >= 0.999, (err, cos)
     assert min(coss.values()) >= 0.98, coss
