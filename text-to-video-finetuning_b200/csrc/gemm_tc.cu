@@ -73,6 +73,16 @@ __device__ __forceinline__ void issue_boxes(const TmaOperand& op, const int32_t*
 // strided in global memory, so every 32-column chunk goes through a per-warp swizzled staging tile and is moved with
 // 16 bytes per lane covering whole rows (full 64/128-byte segments); the residual comes in the same way.  The per-column
 // bias is fetched with one coalesced load per chunk and broadcast through shared memory.
+// flags of the epilogue fast path: known at compile time (folded away) or only at run time (the catch-all instantiation)
+template <bool V>
+struct ConstFlag {
+    __device__ constexpr operator bool() const { return V; }
+};
+struct RuntimeFlag {
+    bool v;
+    __device__ constexpr operator bool() const { return v; }
+};
+
 template <int ESZ>
 __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp, uint32_t lane, uint32_t tmem_base,
                                              uint64_t* acc_full, uint64_t* acc_empty, uint8_t* stg_base) {
@@ -200,104 +210,123 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
             const float bcur = bq0;          // this chunk's per-column term; keep the pipeline two chunks deep
             bq0 = bq1;
             if (ch + 2 < c_end) bq1 = load_colterm(ch + 2);
-            uint4 rcur[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) rcur[i] = rq[i];
-            if (res_pref && ch + 1 < c_end) load_res(ch + 1, rq);
             const bool colterm = has_bias || rb_uniform;
             if (all_rows && cvalid == 32) {
-                // ---- fast path: a full 32 x 32 chunk, every row in bounds - straight-line code, no per-row predicates
-                if (colterm) sbias[lane] = bcur;
-                if (has_res) {   // residual (prefetched): registers -> staging
+                // ---- fast path: a full 32 x 32 chunk, every row in bounds.  The body is instantiated per combination of
+                // (column term, residual, statistics, alpha, per-row time embedding) so that each instantiation is
+                // straight-line code without flag tests: ncu counted 334 warp-instructions per chunk in the flag-driven
+                // version, a third of them predicate bookkeeping (profiles/r2_ncu_full_gemm_ff_proj_before.txt).
+                auto fast = [&](auto kCol, auto kRes, auto kStats, auto kAlpha, auto kRowRb) {
+                    // each flag is a ConstFlag (folded at compile time) or a RuntimeFlag (the catch-all instantiation)
+                    const bool COL = kCol, RES = kRes, STATS = kStats, ALPHA = kAlpha, ROWRB = kRowRb;
+                    if (COL) sbias[lane] = bcur;
+                    if (RES) {   // residual (prefetched one chunk ago): registers -> staging, then fetch the next chunk's
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) sts128(w_res[i], rcur[i]);
-                }
-                tmem_ld_wait();
-                float v[32];
-                if (alpha_one) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * p.alpha;
-                }
-                if (ch + 1 < c_end) tmem_ld32(taddr + (ch + 1) * 32, acc);
-                __syncwarp();
-                if (colterm) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 b = *reinterpret_cast<const float4*>(sbias + 4 * j);  // shared-memory broadcast
-                        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                        for (int i = 0; i < 4; ++i) sts128(w_res[i], rq[i]);
+                        if (ch + 1 < c_end) load_res(ch + 1, rq);
                     }
-                }
-                if (has_rb && !rb_uniform) {
-                    const float4* b4 = reinterpret_cast<const float4*>(p.rowbias + (gn / p.rb_div) * p.rb_ld + col);
+                    tmem_ld_wait();
+                    float* v = reinterpret_cast<float*>(acc);   // in place: the accumulator registers are not reloaded until the
+                    if (ALPHA) {                      // values have been packed into the staging tile
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 b = __ldg(b4 + j);
-                        v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                        for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
                     }
-                }
-                if (has_res) {
+                    if (COL || RES) __syncwarp();
+                    if (COL) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint4 q = lds128(r_res[j]);
-                        v[8 * j + 0] += bf16_lo(q.x); v[8 * j + 1] += bf16_hi(q.x);
-                        v[8 * j + 2] += bf16_lo(q.y); v[8 * j + 3] += bf16_hi(q.y);
-                        v[8 * j + 4] += bf16_lo(q.z); v[8 * j + 5] += bf16_hi(q.z);
-                        v[8 * j + 6] += bf16_lo(q.w); v[8 * j + 7] += bf16_hi(q.w);
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b = *reinterpret_cast<const float4*>(sbias + 4 * j);  // shared-memory broadcast
+                            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                        }
                     }
-                    __syncwarp();
-                }
-                if (ESZ == 2) {
+                    if (ROWRB) {
+                        const float4* b4 = reinterpret_cast<const float4*>(p.rowbias + (gn / p.rb_div) * p.rb_ld + col);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 q;
-                        q.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
-                        q.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-                        q.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-                        q.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-                        sts128(w_own[j], q);
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b = __ldg(b4 + j);
+                            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                        }
                     }
-                } else {
+                    if (RES) {
 #pragma unroll
-                    for (int j = 0; j < CPR; ++j)
-                        sts128(w_own[j], make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
-                                                    __float_as_uint(v[4 * j + 3])));
-                }
-                __syncwarp();
-                if (ESZ == 2 && has_stats) {   // GroupNorm statistics of the staged bf16 tile (see the general path below)
-                    const uint32_t half = lane >> 4, cw = lane & 15u;
-                    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int r = half ? 16 + ((i + 1) & 15) : i;
-                        const uint32_t w = lds32(stg_s + phys(r, int(cw >> 2), 4) + (cw & 3u) * 4u);
-                        const float lo = bf16_lo(w), hi = bf16_hi(w);
-                        s0 += lo; q0 += lo * lo;
-                        s1 += hi; q1 += hi * hi;
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 q = lds128(r_res[j]);
+                            v[8 * j + 0] += bf16_lo(q.x); v[8 * j + 1] += bf16_hi(q.x);
+                            v[8 * j + 2] += bf16_lo(q.y); v[8 * j + 3] += bf16_hi(q.y);
+                            v[8 * j + 4] += bf16_lo(q.z); v[8 * j + 5] += bf16_hi(q.z);
+                            v[8 * j + 6] += bf16_lo(q.w); v[8 * j + 7] += bf16_hi(q.w);
+                        }
+                        __syncwarp();
                     }
-                    if (p.st_seg == 32) {
-                        s0 += __shfl_xor_sync(0xffffffffu, s0, 16); q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
-                        s1 += __shfl_xor_sync(0xffffffffu, s1, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
-                    }
-                    if (p.st_seg == 16 || half == 0) red_add_f32x4(p.stats + (st_off + col + 2 * cw) * 2, s0, q0, s1, q1);
-                }
-                // staging -> global: 16 bytes per lane, whole row segments
-                char* ob = static_cast<char*>(p.out) + (static_cast<int64_t>(col) + sj * EPC) * ESZ;
+                    if constexpr (ESZ == 2) {
 #pragma unroll
-                for (int i = 0; i < CPR; ++i) {
-                    const uint4 q = lds128(r_mov[i]);
-                    char* o = ob + off_s[i] * ESZ;
-                    if (ESZ == 2 || p.out_mode == OUT_F32) {
-                        *reinterpret_cast<uint4*>(o) = q;
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 q;
+                            q.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+                            q.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+                            q.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+                            q.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+                            sts128(w_own[j], q);
+                        }
                     } else {
-                        red_add_f32x4(reinterpret_cast<float*>(o), __uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z),
-                                      __uint_as_float(q.w));
+#pragma unroll
+                        for (int j = 0; j < CPR; ++j) sts128(w_own[j], make_uint4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]));
+                    }
+                    if (ch + 1 < c_end) tmem_ld32(taddr + (ch + 1) * 32, acc);   // next chunk: in flight during the store phase
+                    __syncwarp();
+                    if (ESZ == 2 && STATS) {   // GroupNorm statistics of the staged bf16 tile (see the general path below)
+                        const uint32_t half = lane >> 4, cw = lane & 15u;
+                        float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int r = half ? 16 + ((i + 1) & 15) : i;
+                            const uint32_t w = lds32(stg_s + phys(r, int(cw >> 2), 4) + (cw & 3u) * 4u);
+                            const float lo = bf16_lo(w), hi = bf16_hi(w);
+                            s0 += lo; q0 += lo * lo;
+                            s1 += hi; q1 += hi * hi;
+                        }
+                        if (p.st_seg == 32) {
+                            s0 += __shfl_xor_sync(0xffffffffu, s0, 16); q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
+                            s1 += __shfl_xor_sync(0xffffffffu, s1, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+                        }
+                        if (p.st_seg == 16 || half == 0) red_add_f32x4(p.stats + (st_off + col + 2 * cw) * 2, s0, q0, s1, q1);
+                    }
+                    // staging -> global: 16 bytes per lane, whole row segments
+                    char* ob = static_cast<char*>(p.out) + (static_cast<int64_t>(col) + sj * EPC) * ESZ;
+#pragma unroll
+                    for (int i = 0; i < CPR; ++i) {
+                        const uint4 q = lds128(r_mov[i]);
+                        char* o = ob + off_s[i] * ESZ;
+                        if (ESZ == 2 || p.out_mode == OUT_F32) {
+                            *reinterpret_cast<uint4*>(o) = q;
+                        } else {
+                            red_add_f32x4(reinterpret_cast<float*>(o), __uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z),
+                                          __uint_as_float(q.w));
+                        }
+                    }
+                };
+                using T = ConstFlag<true>;
+                using F = ConstFlag<false>;
+                const bool row_rb = has_rb && !rb_uniform;
+                const int key = (colterm ? 1 : 0) | (has_res ? 2 : 0) | ((ESZ == 2 && has_stats) ? 4 : 0) | (alpha_one ? 0 : 8) | (row_rb ? 16 : 0);
+                switch (key) {
+                    case 0: fast(F{}, F{}, F{}, F{}, F{}); break;     // plain (dgrad, attention products)
+                    case 1: fast(T{}, F{}, F{}, F{}, F{}); break;     // bias (+ folded time embedding)
+                    case 2: fast(F{}, T{}, F{}, F{}, F{}); break;     // residual
+                    case 3: fast(T{}, T{}, F{}, F{}, F{}); break;     // bias + residual
+                    case 4: fast(F{}, F{}, T{}, F{}, F{}); break;     // ... the same with GroupNorm statistics
+                    case 5: fast(T{}, F{}, T{}, F{}, F{}); break;
+                    case 6: fast(F{}, T{}, T{}, F{}, F{}); break;
+                    case 7: fast(T{}, T{}, T{}, F{}, F{}); break;
+                    default: {                                         // alpha != 1 / per-row time embedding: rare, runtime flags
+                        using R = RuntimeFlag;
+                        fast(R{colterm}, R{has_res}, R{ESZ == 2 && has_stats}, R{!alpha_one}, R{row_rb});
+                        break;
                     }
                 }
                 continue;
             }
+            if (res_pref && ch + 1 < c_end) load_res(ch + 1, rq);   // keep the residual pipeline primed for a following fast chunk
             const float bval = bcur;   // bias (+ the warp-uniform time-embedding row) of this chunk, fetched two chunks ago
             if (vec && has_res && cvalid > 0) {         // residual: coalesced global -> staging (bf16, 4 chunks per row)
 #pragma unroll

@@ -22,22 +22,28 @@ for w in want:
         print(f"{w} [{units[i]}] = {k[i]}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-if rows:
-    h = rows[0]
-    def col(name):
-        for i, c in enumerate(h):
-            if c.strip().startswith(name):
-                return i
-        return None
-    ci, cs, ce = col("Source"), col("# Samples") or col("Warp Stall Sampling (All"), col("Instructions Executed")
-    if ci is not None and cs is not None:
-        items = []
-        for r in rows[1:]:
-            try:
-                items.append((float(r[cs]), r[ci], r[ce] if ce is not None else ""))
-            except (ValueError, IndexError):
-                pass
-        tot = sum(x[0] for x in items)
-        print("\n# top stall sites (SASS, warp-state samples), total", tot)
-        for s, ins, ex in sorted(items, reverse=True)[:14]:
-            print(f"  {int(s):6d} {ins[:90]:90s} ex={ex}")
+hi = next((i for i, r in enumerate(rows) if "Source" in r and "# Samples" in r), None)
+if hi is not None:
+    import collections
+    h = rows[hi]
+    ci, cs, ce = h.index("Source"), h.index("# Samples"), h.index("Instructions Executed")
+    stall_cols = [i for i, c in enumerate(h) if c.startswith("stall_") and "Not Issued" not in c]
+    items = []
+    for r in rows[hi + 1:]:
+        try:
+            items.append((float(r[cs]), r[ci].strip(), float(r[ce]), {h[i]: float(r[i]) for i in stall_cols if float(r[i]) > 0}))
+        except (ValueError, IndexError):
+            pass
+    tot, totex = sum(x[0] for x in items), sum(x[2] for x in items)
+    print(f"\n# top stall sites (SASS, warp-state samples): {int(tot)} samples, {int(totex)} warp-instructions executed")
+    for s, ins, ex, st in sorted(items, key=lambda x: -x[0])[:16]:
+        top = ", ".join(f"{k} {int(v)}" for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:2])
+        print(f"  {int(s):6d} {ins[:72]:72s} ex={int(ex):8d}  [{top}]")
+    mix = collections.Counter()
+    for s, ins, ex, st in items:
+        parts = ins.split()
+        if parts:
+            op = parts[1] if parts[0].startswith("@") and len(parts) > 1 else parts[0]
+            mix[op.split(".")[0]] += ex
+    print("\n# instruction mix (warp-instructions executed)")
+    print("  " + "  ".join(f"{op} {100 * n / totex:.1f}%" for op, n in mix.most_common(16)))
