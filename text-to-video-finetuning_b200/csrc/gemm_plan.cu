@@ -64,6 +64,7 @@ Tiling choose_tiling(const int row_dims[3], int ncols, bool mn_major_b, int kblo
                      int* splits_out = nullptr) {
     const int sms = device_sm_count();
     const int forced_bn = env_int("T2V_FORCE_BN"), forced_mh = env_int("T2V_FORCE_MH");
+    const int forced_s = splits_out ? env_int("T2V_FORCE_FWD_SPLITS") : 0;   // sweep hook (tools/plan_sweep.py)
     Tiling best{16, 1, -1};
     double best_cost = 1e30;
     for (int mh = 1; mh <= 2; ++mh) {
@@ -92,10 +93,11 @@ Tiling choose_tiling(const int row_dims[3], int ncols, bool mn_major_b, int kblo
             const int budget = 232448 - 1024 - 256 - kEpilogueStagingBytes;
             if (budget / stage_bytes < 3) continue;
             const int64_t base_tiles = m_tiles * ((ncols + bn - 1) / bn) * extra;
-            const int max_s = (splits_out && base_tiles * 2 <= sms && kblocks >= 8) ? std::min(kblocks / 4, 64) : 1;
+            int max_s = (splits_out && base_tiles * 2 <= sms && kblocks >= 8) ? std::min(kblocks / 4, 64) : 1;
+            if (forced_s) max_s = std::min(forced_s, kblocks);
             for (int s = 1; s <= max_s; ++s) {
                 const int kper = (kblocks + s - 1) / s;
-                if ((kblocks + kper - 1) / kper != s) continue;  // same schedule as a smaller s
+                if (forced_s ? s != max_s : (kblocks + kper - 1) / kper != s) continue;  // same schedule as a smaller s
                 const int64_t tiles = base_tiles * s;
                 const int64_t waves = (tiles + sms - 1) / sms;
                 const double active = double(std::min<int64_t>(tiles, sms));

@@ -89,6 +89,38 @@ __global__ void __launch_bounds__(384, 2) gn_stream_kernel(const GnArgs g) {
     float* t1 = t0 + G;          // [G]  fwd: group rstd   bwd: sum_c gamma * sum dz*xhat
     float a[8], b[8], gam[8];
 
+    // backward modes: saved per-channel coefficients (independent of the prologue below: fetched ahead of it)
+    float mean[8], rstd[8];
+    if (kBwd) {
+        const float4* ab4 = reinterpret_cast<const float4*>(g.ab + (int64_t(s) * C + cv * 8) * 2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 q = __ldg(ab4 + j);
+            a[2 * j] = q.x; b[2 * j] = q.y; a[2 * j + 1] = q.z; b[2 * j + 1] = q.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = cv * 8 + j;
+            mean[j] = __ldg(g.stat + (int64_t(s) * G + c / cpg) * 2);
+            rstd[j] = __ldg(g.stat + (int64_t(s) * G + c / cpg) * 2 + 1);
+        }
+    }
+    // apply modes: this thread's first pixels do not depend on the statistics - their loads are issued now and land while the
+    // block finalises its sample's statistics (two dependent L2 round trips and two barriers)
+    constexpr int UA = MODE == GN_FWD_APPLY ? 4 : 2;
+    uint4 fx[UA], fd[UA];
+    if (!kSums) {
+#pragma unroll
+        for (int u = 0; u < UA; ++u) {
+            if (pl + u * lanes < np) {
+                fx[u] = __ldg(xs + (pl + u * lanes) * V);
+                if (MODE == GN_BWD_APPLY) {
+                    fd[u] = __ldg(ds + (pl + u * lanes) * V);
+                }
+            }
+        }
+    }
+
     if (!kSums) {
         // ---- finalise this sample's statistics (redundantly per block: C values from L2, one round trip)
 #pragma unroll
@@ -186,7 +218,10 @@ __global__ void __launch_bounds__(384, 2) gn_stream_kernel(const GnArgs g) {
             }
             return pack8(v);
         };
-        for (int p = pl, off = pl * V; p < np; p += 4 * lanes, off += 4 * stepv) {   // four pixels in flight, predicated tail
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (pl + u * lanes < np) os[(pl + u * lanes) * V] = apply(fx[u]);
+        for (int p = pl + 4 * lanes, off = p * V; p < np; p += 4 * lanes, off += 4 * stepv) {   // four pixels in flight, predicated tail
             uint4 qx[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u)
@@ -198,22 +233,6 @@ __global__ void __launch_bounds__(384, 2) gn_stream_kernel(const GnArgs g) {
         return;
     }
 
-    // backward modes and the forward sums: saved per-channel coefficients
-    float mean[8], rstd[8];
-    if (kBwd) {
-        const float4* ab4 = reinterpret_cast<const float4*>(g.ab + (int64_t(s) * C + cv * 8) * 2);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 q = __ldg(ab4 + j);
-            a[2 * j] = q.x; b[2 * j] = q.y; a[2 * j + 1] = q.z; b[2 * j + 1] = q.w;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = cv * 8 + j;
-            mean[j] = __ldg(g.stat + (int64_t(s) * G + c / cpg) * 2);
-            rstd[j] = __ldg(g.stat + (int64_t(s) * G + c / cpg) * 2 + 1);
-        }
-    }
     if (kSums) {
         for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
         __syncthreads();
@@ -309,7 +328,10 @@ __global__ void __launch_bounds__(384, 2) gn_stream_kernel(const GnArgs g) {
         return pack8(v);
     };
     const uint4 zero = make_uint4(0, 0, 0, 0);
-    for (int p = pl, off = pl * V; p < np; p += 2 * lanes, off += 2 * stepv) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+        if (pl + u * lanes < np) os[(pl + u * lanes) * V] = apply(fx[u], fd[u], as ? __ldg(as + (pl + u * lanes) * V) : zero);
+    for (int p = pl + 2 * lanes, off = p * V; p < np; p += 2 * lanes, off += 2 * stepv) {
         uint4 qx[2], qd[2], qa[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -336,6 +358,14 @@ __global__ void ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* 
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
     const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    // software pipeline over this warp's rows: the next row's vectors are in flight while the current row is reduced
+    uint4 nx[VPL];
+    auto fetch = [&](int64_t row) {
+#pragma unroll
+        for (int k = 0; k < VPL; ++k)
+            if (lane + 32 * k < V) nx[k] = __ldg(reinterpret_cast<const uint4*>(x + row * C) + lane + 32 * k);
+    };
+    if (warp < rows) fetch(warp);
     for (int64_t row = warp; row < rows; row += nwarps) {
         float v[VPL][8];
         float sum = 0.f;
@@ -343,11 +373,12 @@ __global__ void ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* 
         for (int k = 0; k < VPL; ++k) {
             const int cv = lane + 32 * k;
             if (cv < V) {
-                unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * C) + cv), v[k]);
+                unpack8(nx[k], v[k]);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) sum += v[k][j];
             }
         }
+        if (row + nwarps < rows) fetch(row + nwarps);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         const float mean = sum / C;
@@ -383,8 +414,11 @@ __global__ void ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* 
 }
 
 // dx = rstd (dy g - mean_c(dy g) - xhat mean_c(dy g xhat)) (+ add); dgamma += sum_rows dy xhat; dbeta += sum_rows dy.
+// Register budget: the per-lane parameter-gradient accumulators (16 VPL floats) are the only fp32 arrays that live across rows;
+// the row itself stays packed (bf16, as loaded) and is unpacked twice - once for the row sums, once for dx - and gamma comes
+// from L1 each time, so two 256-thread blocks stay resident per SM up to C = 640.
 template <int VPL>
-__global__ void ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+__global__ void __launch_bounds__(256, VPL <= 3 ? 2 : 1) ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                               const float* __restrict__ gamma, const float* __restrict__ stat,
                               const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ dx,
                               float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int C) {
@@ -393,37 +427,54 @@ __global__ void ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bf
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
     const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
-    float gacc[VPL][8], bacc[VPL][8], gam[VPL][8];
+    float gacc[VPL][8], bacc[VPL][8];
 #pragma unroll
     for (int k = 0; k < VPL; ++k)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            gacc[k][j] = bacc[k][j] = 0.f;
-            const int cv = lane + 32 * k;
-            gam[k][j] = cv < V ? __ldg(gamma + cv * 8 + j) : 0.f;
+        for (int j = 0; j < 8; ++j) gacc[k][j] = bacc[k][j] = 0.f;
+    // software pipeline over this warp's rows: x, dy and the saved statistics of the next row are in flight while the
+    // current row is reduced; the residual-gradient vector (`add`) of the current row is fetched ahead of the reductions
+    uint4 nx[VPL], nd[VPL];
+    float2 nst = make_float2(0.f, 0.f);
+    auto fetch = [&](int64_t row) {
+        nst = __ldg(reinterpret_cast<const float2*>(stat) + row);
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            if (lane + 32 * k < V) {
+                nx[k] = __ldg(reinterpret_cast<const uint4*>(x + row * C) + lane + 32 * k);
+                nd[k] = __ldg(reinterpret_cast<const uint4*>(dy + row * C) + lane + 32 * k);
+            }
         }
+    };
+    if (warp < rows) fetch(warp);
     for (int64_t row = warp; row < rows; row += nwarps) {
-        const float mean = stat[row * 2], rstd = stat[row * 2 + 1];
-        float xh[VPL][8], dg[VPL][8];
+        const float mean = nst.x, rstd = nst.y;
+        uint4 cx[VPL], cd[VPL], ra[VPL];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int k = 0; k < VPL; ++k) {
             const int cv = lane + 32 * k;
             if (cv < V) {
+                cx[k] = nx[k];
+                cd[k] = nd[k];
+                if (add) ra[k] = __ldg(reinterpret_cast<const uint4*>(add + row * C) + cv);
                 float v[8], d[8];
-                unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * C) + cv), v);
-                unpack8(__ldg(reinterpret_cast<const uint4*>(dy + row * C) + cv), d);
+                unpack8(cx[k], v);
+                unpack8(cd[k], d);
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + cv * 2), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + cv * 2 + 1);
+                const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    xh[k][j] = (v[j] - mean) * rstd;
-                    dg[k][j] = d[j] * gam[k][j];
-                    s1 += dg[k][j];
-                    s2 += dg[k][j] * xh[k][j];
-                    gacc[k][j] += d[j] * xh[k][j];
+                    const float xh = (v[j] - mean) * rstd;
+                    const float dg = d[j] * gm[j];
+                    s1 += dg;
+                    s2 += dg * xh;
+                    gacc[k][j] += d[j] * xh;
                     bacc[k][j] += d[j];
                 }
             }
         }
+        if (row + nwarps < rows) fetch(row + nwarps);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             s1 += __shfl_xor_sync(0xffffffffu, s1, o);
@@ -435,11 +486,16 @@ __global__ void ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bf
         for (int k = 0; k < VPL; ++k) {
             const int cv = lane + 32 * k;
             if (cv < V) {
-                float o[8], r[8];
-                if (add) unpack8(__ldg(reinterpret_cast<const uint4*>(add + row * C) + cv), r);
+                float v[8], d[8], o[8], r[8];
+                unpack8(cx[k], v);
+                unpack8(cd[k], d);
+                if (add) unpack8(ra[k], r);
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + cv * 2), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + cv * 2 + 1);
+                const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    o[j] = rstd * (dg[k][j] - s1 - xh[k][j] * s2);
+                    const float xh = (v[j] - mean) * rstd;
+                    o[j] = rstd * (d[j] * gm[j] - s1 - xh * s2);
                     if (add) o[j] += r[j];
                 }
                 reinterpret_cast<uint4*>(dx + row * C)[cv] = pack8(o);
@@ -470,14 +526,17 @@ __global__ void ln_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bf
 
 static size_t gn_smem(int C, int G) { return size_t(2 * C + 2 * G) * sizeof(float); }
 
-// Streaming geometry: threads = V * lanes (<= 256, or V itself up to 384 for the 2560- / 3072-channel concatenations), a block owns `chunk_pixels` pixels of one sample.  Apply modes want
-// several blocks per SM (their latency chains overlap) with at least four pixels per thread in flight; sums modes pay 2C
-// atomics per block, so they use fewer, longer blocks.
-static void gn_plan(GnArgs& g, int S, bool sums) {
+// Streaming geometry: threads = V * lanes (<= 256, or V itself up to 384 for the 2560- / 3072-channel concatenations), a
+// block owns `chunk_pixels` pixels of one sample.  Apply modes: exactly ONE wave of blocks - as many as are resident at once
+// (`resident` per SM, from the occupancy calculator) - so that every block's latency chain (statistics -> coefficients ->
+// first pixels) overlaps its neighbours' streaming and no partial second wave pays that chain again (4 x SMs blocks with 3
+// resident per SM ran as 1.33 waves = 2 block times).  Sums modes pay 2C atomics per block: fewer, longer blocks.
+static void gn_plan(GnArgs& g, int S, bool sums, int resident) {
     const int V = g.C / 8;
     g.lanes = std::max(1, 256 / V);
     const int sms = device_sm_count();
-    const int64_t want = std::max<int64_t>(1, ((sums ? 2 : 4) * sms + S - 1) / S);
+    const int64_t blocks = sums ? 2 * int64_t(sms) : int64_t(std::max(1, resident)) * sms;
+    const int64_t want = sums ? std::max<int64_t>(1, (blocks + S - 1) / S) : std::max<int64_t>(1, blocks / S);
     const int64_t min_px = int64_t(g.lanes) * (sums ? 8 : 4);
     const int64_t cp = std::max<int64_t>(min_px, (g.P + want - 1) / want);
     g.chunk_pixels = int(std::min<int64_t>(cp, g.P));
@@ -490,11 +549,28 @@ static int gn_check(const GnArgs& g) {
     return 0;
 }
 
+// resident blocks per SM of gn_stream_kernel<MODE> for a block size (cached: the occupancy query is a driver call)
+template <int MODE>
+static int gn_resident(int threads, size_t smem) {
+    static std::mutex mu;
+    static int cache[13] = {};   // index: warps per block (threads <= 384)
+    const int w = (threads + 31) / 32;
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache[w] == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gn_stream_kernel<MODE>, threads, smem) != cudaSuccess || n < 1) n = 2;
+        cache[w] = n;
+    }
+    return cache[w];
+}
+
 template <int MODE>
 static int gn_stream(GnArgs& g, int S, cudaStream_t st) {
     const bool sums = MODE == GN_BWD_SUMS || MODE == GN_FWD_SUMS;
-    gn_plan(g, S, sums);
-    return int(launch_pdl(gn_stream_kernel<MODE>, dim3(S * g.chunks), dim3((g.C / 8) * g.lanes), gn_smem(g.C, g.G), st, g));
+    const int V = g.C / 8;
+    const int threads = V * std::max(1, 256 / V);
+    gn_plan(g, S, sums, sums ? 0 : gn_resident<MODE>(threads, gn_smem(g.C, g.G)));
+    return int(launch_pdl(gn_stream_kernel<MODE>, dim3(S * g.chunks), dim3(V * g.lanes), gn_smem(g.C, g.G), st, g));
 }
 
 // Standalone per-sample channel sums of x [S][P][C] into stats (+=), row pitch ld channels.  Used by t2v_channel_stats and
@@ -507,6 +583,34 @@ int launch_channel_stats(const void* x, float* stats, int S, int64_t P, int C, i
     g.P = P; g.C = C; g.G = 1;
     if (int r = gn_check(g)) return r;
     return gn_stream<GN_FWD_SUMS>(g, S, st);
+}
+
+// Resident 256-thread blocks per SM of the LayerNorm kernels (occupancy calculator, cached per VPL): the grids are ONE wave of
+// persistent blocks whose warps stride over the rows - a partial second wave would start only when first-wave blocks retire.
+static int ln_resident(bool bwd, int vpl, size_t smem) {
+    static std::mutex mu;
+    static int cache[2][9] = {};
+    vpl = std::min(std::max(vpl, 1), 8);
+    std::lock_guard<std::mutex> lock(mu);
+    int& c = cache[bwd ? 1 : 0][vpl];
+    if (c == 0) {
+        int n = 0;
+        cudaError_t e = cudaErrorUnknown;
+#define LN_OCC(K) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, K, 256, smem)
+        switch (vpl) {
+            case 1: if (bwd) LN_OCC(ln_bwd_kernel<1>); else LN_OCC(ln_fwd_kernel<1>); break;
+            case 2: if (bwd) LN_OCC(ln_bwd_kernel<2>); else LN_OCC(ln_fwd_kernel<2>); break;
+            case 3: if (bwd) LN_OCC(ln_bwd_kernel<3>); else LN_OCC(ln_fwd_kernel<3>); break;
+            case 4: if (bwd) LN_OCC(ln_bwd_kernel<4>); else LN_OCC(ln_fwd_kernel<4>); break;
+            case 5: if (bwd) LN_OCC(ln_bwd_kernel<5>); else LN_OCC(ln_fwd_kernel<5>); break;
+            case 6: if (bwd) LN_OCC(ln_bwd_kernel<6>); else LN_OCC(ln_fwd_kernel<6>); break;
+            case 7: if (bwd) LN_OCC(ln_bwd_kernel<7>); else LN_OCC(ln_fwd_kernel<7>); break;
+            default: if (bwd) LN_OCC(ln_bwd_kernel<8>); else LN_OCC(ln_fwd_kernel<8>); break;
+        }
+#undef LN_OCC
+        c = (e == cudaSuccess && n >= 1) ? n : (bwd ? 2 : 4);
+    }
+    return c;
 }
 
 }  // namespace t2v
@@ -584,7 +688,7 @@ int t2v_layernorm_fwd(const void* x, const float* gamma, const float* beta, void
     if (C % 8 || C > 2048) return fail(-2, "layernorm: C=%d unsupported (multiple of 8, <= 2048)", C);
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     const int vpl = (C / 8 + 31) / 32;
-    const int grid = int(std::min<int64_t>((rows + 7) / 8, 148 * 8));
+    const int grid = int(std::min<int64_t>((rows + 7) / 8, int64_t(device_sm_count()) * ln_resident(false, vpl, 0)));
     LN_DISPATCH(ln_fwd_kernel, grid, 0, st, static_cast<const __nv_bfloat16*>(x), gamma, beta, static_cast<__nv_bfloat16*>(y), stat,
                 rows, C, eps);
     return launch_checked(int(cudaGetLastError()), "layernorm_fwd");
@@ -595,7 +699,7 @@ int t2v_layernorm_bwd(const void* dy, const void* x, const float* gamma, const f
     if (C % 8 || C > 2048) return fail(-2, "layernorm: C=%d unsupported (multiple of 8, <= 2048)", C);
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     const int vpl = (C / 8 + 31) / 32;
-    const int grid = int(std::min<int64_t>((rows + 7) / 8, 148 * 2));
+    const int grid = int(std::min<int64_t>((rows + 7) / 8, int64_t(device_sm_count()) * ln_resident(true, vpl, 2 * C * sizeof(float))));
     LN_DISPATCH(ln_bwd_kernel, grid, 2 * C * sizeof(float), st, static_cast<const __nv_bfloat16*>(x),
                 static_cast<const __nv_bfloat16*>(dy), gamma, stat, static_cast<const __nv_bfloat16*>(add),
                 static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, rows, C);
