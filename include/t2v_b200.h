@@ -92,6 +92,14 @@ int64_t t2v_conv_workspace_bytes(int32_t dgrad, int32_t N, int32_t H, int32_t W,
 int t2v_conv_wgrad(const void* x, const void* dy, float* dw, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
                    int32_t KH, int32_t KW, int32_t stride, int32_t pad_h0, int32_t pad_h1, int32_t pad_w0,
                    int32_t pad_w1, void* stream);
+/* The same plus the bias gradient of the layer: dbias [Cout] (fp32) += sum over output pixels of dy - what autograd's
+ * conv / linear backward returns as grad_bias (reference: every biased Conv2d / Conv3d / Linear of models/unet_3d_*.py).
+ * The sums come out of the same launch (an extra 16-column MMA of the dy tile against a tile of ones, added from the
+ * epilogue with red.global.add.f32) unless the chosen tiling has no spare accumulator columns; then a column-sum pass
+ * over dy follows.  dbias == NULL is t2v_conv_wgrad.                                                               */
+int t2v_conv_wgrad_bias(const void* x, const void* dy, float* dw, float* dbias, int32_t N, int32_t H, int32_t W, int32_t Cin,
+                        int32_t Cout, int32_t KH, int32_t KW, int32_t stride, int32_t pad_h0, int32_t pad_h1, int32_t pad_w0,
+                        int32_t pad_w1, void* stream);
 
 /* Strided-batched GEMM on the same kernel:  C[z1][z2] = alpha * opA(A[z1][z2]) * opB(B[z1][z2])^T  (+= if accumulate)
  *   a_kmajor=1: A is [M][K] rows (K contiguous);  a_kmajor=0: A is stored [K][M] (M contiguous)

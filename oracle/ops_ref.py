@@ -65,11 +65,13 @@ def conv_dgrad(dy, w, in_hw, stride=1, pads=(0, 0, 0, 0), residual=None):
 
 
 @torch.enable_grad()
-def conv_wgrad(x, dy, dw, stride=1, pads=(0, 0, 0, 0)):
+def conv_wgrad(x, dy, dw, stride=1, pads=(0, 0, 0, 0), dbias=None):
     w = torch.zeros(dw.shape, dtype=torch.float32, device=x.device, requires_grad=True)
     y = _conv_f32(x, w, stride, pads)
     (g,) = torch.autograd.grad(y, w, dy.float())
     dw += g
+    if dbias is not None:
+        dbias += dy.float().reshape(-1, dy.shape[-1]).sum(0)
 
 
 def _strided(t, sizes, strides):

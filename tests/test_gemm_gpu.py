@@ -111,6 +111,47 @@ def test_conv_dgrad_wgrad(case):
     assert e < 2e-3, f"wgrad rel err {e}"
 
 
+WGRAD_BIAS_CASES = [
+    # (conv case, forced UMMA N, forced row halves): every placement of the row-sum accumulator and the fallback
+    ((16, 32, 32, 320, 320, 3, 3, 1, (1, 1, 1, 1)), 0, 0),     # planner's own choice (split-K, Cout ragged against 128-row tiles)
+    ((1, 1, 4096, 640, 640, 1, 1, 1, (0, 0, 0, 0)), 160, 1),   # 128-row tiles, columns [160, 192) of a 256-column stage
+    ((1, 1, 4096, 640, 640, 1, 1, 1, (0, 0, 0, 0)), 96, 2),    # 256-row tiles, two 128-column halves
+    ((1, 1, 4096, 640, 640, 1, 1, 1, (0, 0, 0, 0)), 128, 2),   # 256-row tiles: no room in 128-column halves -> one 2 x 256 stage
+    ((1, 1, 2048, 1280, 320, 1, 1, 1, (0, 0, 0, 0)), 224, 2),  # widest tile that still has 32 spare columns
+    ((1, 1, 2048, 1280, 320, 1, 1, 1, (0, 0, 0, 0)), 256, 1),  # forced 256: the planner's narrow search has no candidate -> column-sum pass
+    ((4, 16, 16, 64, 64, 3, 3, 2, (1, 1, 1, 1)), 0, 0),        # stride 2
+    ((2, 6, 64, 64, 72, 3, 1, 1, (1, 1, 0, 0)), 0, 0),         # temporal conv, Cout = 72 (one ragged row tile)
+    ((1, 3, 40, 192, 160, 1, 1, 1, (0, 0, 0, 0)), 0, 0),
+]
+
+
+@pytest.mark.parametrize("case,bn,mh", WGRAD_BIAS_CASES)
+def test_conv_wgrad_bias(case, bn, mh, monkeypatch):
+    """t2v_conv_wgrad_bias: the weight gradient is unchanged and dbias += column sums of dy (both accumulate)."""
+    nat = _lib()
+    N, H, W, Ci, Co, KH, KW, s, pads = case
+    if bn:
+        monkeypatch.setenv("T2V_FORCE_BN", str(bn))
+    if mh:
+        monkeypatch.setenv("T2V_FORCE_MH", str(mh))
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(N, H, W, Ci, device="cuda", generator=g).bfloat16()
+    Ho = (H + pads[0] + pads[1] - KH) // s + 1
+    Wo = (W + pads[2] + pads[3] - KW) // s + 1
+    dy = (torch.randn(N, Ho, Wo, Co, device="cuda", generator=g) + 0.25).bfloat16()
+    dw_ref = torch.ones(Co, KH, KW, Ci, device="cuda", dtype=torch.float32)
+    nat.check(nat.lib().t2v_conv_wgrad(P(x), P(dy), P(dw_ref), N, H, W, Ci, Co, KH, KW, s, *pads, stream()))
+    dw = torch.ones(Co, KH, KW, Ci, device="cuda", dtype=torch.float32)
+    db = torch.full((Co,), 3.0, device="cuda", dtype=torch.float32)
+    nat.check(nat.lib().t2v_conv_wgrad_bias(P(x), P(dy), P(dw), P(db), N, H, W, Ci, Co, KH, KW, s, *pads, stream()))
+    torch.cuda.synchronize()
+    want = 3.0 + dy.float().reshape(-1, Co).sum(0)
+    e = rel_err(db, want)
+    assert e < 1e-4, f"dbias rel err {e}"      # exact bf16 x 1.0 products, fp32 accumulation: only the summation order differs
+    e = rel_err(dw, dw_ref)
+    assert e < 1e-5, f"wgrad changed by the fused row sums: {e}"   # red.add order of split-K partials only
+
+
 SPLITK_CASES = [
     (16, 4, 4, 640, 640, 3, 3, 1, (1, 1, 1, 1)),        # deepest resnet conv: 2 x 4 output tiles, 90 k-blocks
     (1, 16, 16, 1280, 1280, 3, 1, 1, (1, 1, 0, 0)),     # temporal conv at 4x4: W=H*W, H=F

@@ -578,9 +578,11 @@ int64_t t2v_conv_workspace_bytes(int32_t dgrad, int32_t N, int32_t H, int32_t W,
     return splits > 1 ? int64_t(N) * Ho * Wo * Cout * 4 : 0;
 }
 
-int t2v_conv_wgrad(const void* x, const void* dy, float* dw, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
-                   int32_t KH, int32_t KW, int32_t stride, int32_t pad_h0, int32_t pad_h1, int32_t pad_w0,
-                   int32_t pad_w1, void* stream) {
+// dbias != NULL: the bias gradient dbias[Cout] += sum over output pixels of dy rides in the same launch whenever the tiling
+// leaves 32 spare TMEM columns next to the accumulator (EPI_ROWSUM_A, gemm_tc.cuh); otherwise a column-sum pass follows.
+static int conv_wgrad_impl(const void* x, const void* dy, float* dw, float* dbias, int32_t N, int32_t H, int32_t W, int32_t Cin,
+                           int32_t Cout, int32_t KH, int32_t KW, int32_t stride, int32_t pad_h0, int32_t pad_h1, int32_t pad_w0,
+                           int32_t pad_w1, void* stream) {
     if (int r = check_channels(Cin, "Cin")) return r;
     if (int r = check_channels(Cout, "Cout")) return r;
     if (stride != 1 && stride != 2) return fail(-2, "conv_wgrad: stride %d unsupported", stride);
@@ -600,22 +602,25 @@ int t2v_conv_wgrad(const void* x, const void* dy, float* dw, int32_t N, int32_t 
     // measured configuration on 13 of them): per k-block the slowest of tcgen05 issue, per-SM operand fill (~40 B/clk with
     // MN-major boxes) and chip-wide L2->SM bandwidth (~6000 B/clk); the split-K epilogue pays for its red.global.add
     // traffic at ~2500 B/clk chip-wide.
-    int splits = 1;
-    {
+    struct Choice {
+        Tiling t;
+        int splits;
+        double cost;
+    };
+    auto search = [&](int max_bn) {
         const int sms = device_sm_count();
         const int forced_bn = env_int("T2V_FORCE_BN"), forced_mh = env_int("T2V_FORCE_MH"), forced_s = env_int("T2V_FORCE_SPLITS");
         const int64_t taps = int64_t(KH) * KW;
         const int mt1 = p.tdim[1];
-        Tiling best{16, 1, -1};
-        double best_cost = 1e30;
+        Choice best{Tiling{16, 1, -1}, 1, 1e30};
         for (int mh = 1; mh <= 2; ++mh) {
             if ((forced_mh && mh != forced_mh) || (mh == 2 && mt1 < 2)) continue;
             const int mt = mh == 2 ? (mt1 + 1) / 2 : mt1;
-            for (int bn = 256; bn >= 16; bn -= 16) {
+            for (int bn = max_bn; bn >= 16; bn -= 16) {
                 if (forced_bn && bn != forced_bn) continue;
                 if (bn > 16 && bn - 16 >= Cin) continue;
                 const int stage_bytes = mh * kBlockM * 128 + ((bn + 63) / 64) * 8192;
-                const int budget = 232448 - 1024 - 256 - kEpilogueStagingBytes;
+                const int budget = 232448 - 1024 - 256 - kEpilogueStagingBytes - kOnesTileBytes;
                 if (budget / stage_bytes < 3) continue;
                 const int64_t base = int64_t(mt) * ((Cin + bn - 1) / bn) * taps;
                 for (int s = 1; s <= kb_total && s <= 128; ++s) {
@@ -629,15 +634,30 @@ int t2v_conv_wgrad(const void* x, const void* dy, float* dw, int32_t N, int32_t 
                     const double t_epi = 500.0 + 4.0 * mh * bn;
                     const double red = double(tiles) * mh * kBlockM * bn * 4.0 / 2500.0;
                     const double cost = double(waves) * (kper * t_kb + t_epi) + red;
-                    if (cost < best_cost - 1e-9) {
-                        best_cost = cost;
-                        best = Tiling{bn, mh, mh == 2 ? 1 : -1};
-                        splits = s;
-                    }
+                    if (cost < best.cost - 1e-9) best = Choice{Tiling{bn, mh, mh == 2 ? 1 : -1}, s, cost};
                 }
             }
         }
-        apply_tiling(p, best);
+        return best;
+    };
+    Choice pick = search(256);
+    bool fuse_rowsum = false;
+    if (dbias && !env_int("T2V_NO_ROWSUM_FUSE")) {
+        // the row-sum accumulator needs the 32 TMEM columns after the tile's own: UMMA N <= 224.  A narrower tile is accepted
+        // when it costs less than the separate column-sum launch it saves (launch gap + one pass over dy, ~3000 B/clk).
+        const Choice narrow = pick.t.bn <= 224 ? pick : search(224);
+        const double colsum_cost = 6000.0 + double(N) * Ho * Wo * Cout * 2.0 / 3000.0;
+        if (narrow.cost < 1e29 && narrow.cost <= pick.cost + colsum_cost) {
+            pick = narrow;
+            fuse_rowsum = true;
+        }
+    }
+    int splits = pick.splits;
+    apply_tiling(p, pick.t);
+    if (fuse_rowsum && p.mh == 2 && p.block_n > 96 && p.acc_half_cols == 128) {   // make room: one accumulator stage of 2 x 256 columns
+        p.acc_half_cols = 256;
+        p.acc_stage_cols = 512;
+        p.nacc = 1;
     }
     p.tdim[0] = (Cin + p.block_n - 1) / p.block_n;
     p.kb_per_split = (kb_total + splits - 1) / splits;
@@ -674,7 +694,28 @@ int t2v_conv_wgrad(const void* x, const void* dy, float* dw, int32_t N, int32_t 
     fill_epilogue(p, nullptr, dw, OUT_F32_RED);
     p.alpha = 1.0f;
     set_vec_flag(p);
-    return launch_checked(launch_gemm(p, true, true, static_cast<cudaStream_t>(stream)), "conv_wgrad");
+    if (fuse_rowsum) {
+        p.flags |= EPI_ROWSUM_A;
+        p.rowsum = dbias;
+        p.rowsum_col = static_cast<uint32_t>(p.block_n);
+        const int budget = 232448 - 1024 - 256 - kEpilogueStagingBytes - kOnesTileBytes;
+        p.num_stages = std::min<int>(p.num_stages, budget / (p.stage_bytes_a + p.stage_bytes_b));
+    }
+    if (int r = launch_checked(launch_gemm(p, true, true, static_cast<cudaStream_t>(stream)), "conv_wgrad")) return r;
+    if (dbias && !fuse_rowsum) return t2v_colsum(dy, dbias, 1, int64_t(N) * Ho * Wo, Cout, stream);
+    return 0;
+}
+
+int t2v_conv_wgrad(const void* x, const void* dy, float* dw, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                   int32_t KH, int32_t KW, int32_t stride, int32_t pad_h0, int32_t pad_h1, int32_t pad_w0,
+                   int32_t pad_w1, void* stream) {
+    return conv_wgrad_impl(x, dy, dw, nullptr, N, H, W, Cin, Cout, KH, KW, stride, pad_h0, pad_h1, pad_w0, pad_w1, stream);
+}
+
+int t2v_conv_wgrad_bias(const void* x, const void* dy, float* dw, float* dbias, int32_t N, int32_t H, int32_t W, int32_t Cin,
+                        int32_t Cout, int32_t KH, int32_t KW, int32_t stride, int32_t pad_h0, int32_t pad_h1, int32_t pad_w0,
+                        int32_t pad_w1, void* stream) {
+    return conv_wgrad_impl(x, dy, dw, dbias, N, H, W, Cin, Cout, KH, KW, stride, pad_h0, pad_h1, pad_w0, pad_w1, stream);
 }
 
 int t2v_bgemm(const T2VMat* A, const T2VMat* B, void* C, int64_t ldc, int64_t c_stride_z1, int64_t c_stride_z2,

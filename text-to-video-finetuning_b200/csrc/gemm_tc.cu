@@ -128,6 +128,7 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
     for (int32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         TileVars tv;
         decompose_tile(p, tile, tv);
+        const bool rowsum_tile = (p.flags & EPI_ROWSUM_A) && tv.t[0] == 0 && tv.t[2] == 0 && tv.t[3] == 0 && (p.mh == 2 || grp == 0);
         if (p.mh == 2 && grp == 1) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) tv.t[i] += (i == p.pair_var) ? 1 : 0;
@@ -469,6 +470,13 @@ __device__ __forceinline__ void run_epilogue(const GemmParams& p, uint32_t warp,
                 }
             }
         }
+        if (rowsum_tile) {
+            // row sums of operand A (weight gradient: the bias gradient): 16 identical accumulator columns, column 0 is taken.
+            // mh == 1: both warp groups see all 128 rows (they split the columns) - group 0 alone adds them.
+            tmem_ld32(taddr + p.rowsum_col, acc);
+            tmem_ld_wait();
+            if (row_ok) atomicAdd(p.rowsum + gw, __uint_as_float(acc[0]));
+        }
         tc_fence_before();
         mbar_arrive(&acc_empty[as]);
     }
@@ -480,6 +488,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
     // 1024-byte alignment is required by the 128-byte swizzle atoms.
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int S = p.num_stages;
+    const bool rowsum_a = p.flags & EPI_ROWSUM_A;
+    const uint8_t* ones_tile = smem;              // EPI_ROWSUM_A: 16 rows x 128 bytes of bf16 1.0 (any layout: all elements equal)
+    if (rowsum_a) smem += kOnesTileBytes;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + static_cast<size_t>(S) * p.stage_bytes_a;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + static_cast<size_t>(S) * p.stage_bytes_b);
@@ -506,6 +517,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    if (rowsum_a && warp == 2) {   // the constant B operand of the row-sum MMAs; made visible to the tensor core (async proxy)
+        const uint32_t one2 = 0x3F803F80u;         // two bf16 1.0
+        uint4* o = reinterpret_cast<uint4*>(const_cast<uint8_t*>(ones_tile));
+        for (uint32_t i = lane; i < kOnesTileBytes / 16; i += 32) o[i] = make_uint4(one2, one2, one2, one2);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -576,6 +593,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
         // ------------------------------------------------------------------ MMA issuer
         if (elect_one()) {
             const uint32_t idesc = make_idesc_bf16(static_cast<uint32_t>(p.block_n), A_MN, B_MN);
+            // EPI_ROWSUM_A: D[128 x 16] += A_tile * ones: the same A descriptor against a K-major tile of ones (never advanced
+            // along K - every element is 1.0), accumulated next to the tile's own columns
+            const uint32_t idesc_ones = make_idesc_bf16(16u, A_MN, false);
+            const uint64_t d_ones = make_sw128_desc(smem_u32(ones_tile), 0u, 1024);
             // descriptor advance per UMMA_K=16 step, in 16-byte units
             constexpr uint32_t a_kstep = A_MN ? (16u * 128u) >> 4 : 32u >> 4;
             constexpr uint32_t b_kstep = B_MN ? (16u * 128u) >> 4 : 32u >> 4;
@@ -593,6 +614,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                 mbar_wait(&acc_empty[as], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * p.acc_stage_cols;
+                const bool rowsum_tile = rowsum_a && tv.t[0] == 0 && tv.t[2] == 0 && tv.t[3] == 0;
                 for (int32_t kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -604,6 +626,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_tc_kernel(const __grid_co
                         if (p.mh == 2)  // second 128-row half: same B tile, A half 1 (16 KB further), accumulator half 1
                             umma_f16(tmem_d + p.acc_half_cols, da + ((kBlockM * 128) >> 4) + k * a_kstep, db + k * b_kstep, idesc,
                                      (kb > kb0 || k > 0) ? 1u : 0u);
+                        if (rowsum_tile) {
+                            umma_f16(tmem_d + p.rowsum_col, da + k * a_kstep, d_ones, idesc_ones, (kb > kb0 || k > 0) ? 1u : 0u);
+                            if (p.mh == 2)
+                                umma_f16(tmem_d + p.acc_half_cols + p.rowsum_col, da + ((kBlockM * 128) >> 4) + k * a_kstep, d_ones, idesc_ones,
+                                         (kb > kb0 || k > 0) ? 1u : 0u);
+                        }
                     }
                     umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
                     if (++stage == static_cast<uint32_t>(S)) {
@@ -689,7 +717,7 @@ static int launch_impl(const GemmParams& p, cudaStream_t stream) {
     static std::once_flag attr_once;   // forward runs on the Python thread, backward on autograd worker threads
     static cudaError_t attr_err = cudaSuccess;
     const size_t smem = static_cast<size_t>(p.num_stages) * (p.stage_bytes_a + p.stage_bytes_b) + 1024 /*align*/ + 256 /*barriers*/ +
-                        kEpilogueStagingBytes;
+                        kEpilogueStagingBytes + ((p.flags & EPI_ROWSUM_A) ? kOnesTileBytes : 0);
     auto kern = gemm_tc_kernel<A_MN, B_MN>;
     std::call_once(attr_once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448); });
     if (attr_err != cudaSuccess) return static_cast<int>(attr_err);

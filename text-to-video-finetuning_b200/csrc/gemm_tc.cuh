@@ -47,7 +47,9 @@ enum EpiFlags : int32_t {
     EPI_RESIDUAL = 4,   // + residual[same offset as out]     (bf16)
     EPI_VEC = 8,        // 16-byte vector access is legal for out/residual
     EPI_STATS = 16,     // accumulate per-(frame, channel) sum / sum of squares of the output into `stats` (GroupNorm input statistics)
+    EPI_ROWSUM_A = 32,  // rowsum[row] += sum over K of operand A (weight gradient: A = dy^T, so this is the bias gradient)
 };
+constexpr int kOnesTileBytes = 2048;  // EPI_ROWSUM_A: a 16 x 64 K-major bf16 tile of ones in front of the pipeline stages
 
 struct alignas(64) GemmParams {
     TmaOperand a, b;
@@ -92,7 +94,11 @@ struct alignas(64) GemmParams {
     float* stats;
     int64_t st_ld;
     int32_t st_cw, st_ch, st_cn, st_div, st_seg;
-    int32_t pad3_;
+    // EPI_ROWSUM_A: tiles with t[0] == t[2] == t[3] == 0 issue, next to every main MMA, an N = 16 MMA of the same A tile against
+    // a constant tile of ones; its accumulator (16 identical columns) sits at TMEM column `rowsum_col` of the tile's
+    // accumulator region and the epilogue adds column 0 to rowsum[t[1] * bw + row] (red.add: split-K partials sum up).
+    uint32_t rowsum_col;
+    float* rowsum;
 };
 
 // Launches the kernel (grid = min(num_tiles, #SMs) persistent CTAs).  Returns cudaError_t as int.

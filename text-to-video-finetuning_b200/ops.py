@@ -269,7 +269,9 @@ class _Conv(Function):
         gw = grad_phys(weight) if weight.requires_grad else None
 
         def param_grads():
-            if gb is not None:
+            # the plain bias gradient (column sums of dy) rides in the weight-gradient launch when both are wanted
+            fuse_bias = gb is not None and gw is not None and not (cin_pad or cout_pad) and d_rowbias_full is None
+            if gb is not None and not fuse_bias:
                 if cout_pad:
                     tmp = torch.zeros(Co, device=dy.device, dtype=torch.float32)
                     prims.colsum(dy, tmp.view(1, Co), 1, N * Ho * Wo, Co)
@@ -284,7 +286,7 @@ class _Conv(Function):
                     prims.conv_wgrad(x, dy, tmp, stride, pads)
                     gw.add_(tmp[:gw.shape[0], :, :, :gw.shape[3]])
                 else:
-                    prims.conv_wgrad(x, dy, gw, stride, pads)
+                    prims.conv_wgrad(x, dy, gw, stride, pads, dbias=gb if fuse_bias else None)
 
         if gb is not None or gw is not None:
             _run_param_grads(param_grads, dy, x, d_rowbias_full)

@@ -85,14 +85,19 @@ def conv_dgrad(dy, w, in_hw, stride=1, pads=(0, 0, 0, 0), residual=None):
     return dx
 
 
-def conv_wgrad(x, dy, dw, stride=1, pads=(0, 0, 0, 0)):
-    """dw [Co,KH,KW,Ci] fp32 += dy^T * shifted(x)."""
+def conv_wgrad(x, dy, dw, stride=1, pads=(0, 0, 0, 0), dbias=None):
+    """dw [Co,KH,KW,Ci] fp32 += dy^T * shifted(x);  dbias [Co] fp32 += column sums of dy (the layer's bias gradient, produced by
+    the same launch whenever the tiling allows - include/t2v_b200.h)."""
     _chk_bf16(x, dy)
-    _chk_f32(dw)
+    _chk_f32(dw, dbias)
     N, H, W, Ci = x.shape
     Co, KH, KW, Ci2 = dw.shape
     assert Ci2 == Ci and dy.shape[-1] == Co
-    native.check(native.lib().t2v_conv_wgrad(_p(x), _p(dy), _p(dw), N, H, W, Ci, Co, KH, KW, stride, *pads, _stream()))
+    if dbias is None:
+        native.check(native.lib().t2v_conv_wgrad(_p(x), _p(dy), _p(dw), N, H, W, Ci, Co, KH, KW, stride, *pads, _stream()))
+    else:
+        assert dbias.numel() == Co and dbias.is_contiguous()
+        native.check(native.lib().t2v_conv_wgrad_bias(_p(x), _p(dy), _p(dw), _p(dbias), N, H, W, Ci, Co, KH, KW, stride, *pads, _stream()))
 
 
 def _mat(t, kmajor, ld, s1, s2):
