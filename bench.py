@@ -344,6 +344,9 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=0, help="frames of the CPU clip (reference arm / cpu_baseline); 0 = the workload's")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (and with it the parity check)")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--profile-timed-region", action="store_true",
+                    help="cudaProfilerStart/Stop around the K timed steps: `ncu --profile-from-start off ... python bench.py --steps 1 "
+                         "--profile-timed-region` lists exactly the kernels of the timed region (numbers printed under ncu are not bench values)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.steps is None:
@@ -433,10 +436,11 @@ def main():
         from t2v_b200 import profiling
         calls = profiling.record_calls(lambda: eager(*devin), ["conv_fwd", "conv_dgrad", "conv_wgrad", "bgemm"])
         gemm_ms, gemm_ms_warm, n_gemm = 0.0, 0.0, 0
-        for key, (cnt, _) in calls.items():
-            gemm_ms += profiling.replay_us(key, dev, reps=8, cold=True) * cnt / 1e3
-            gemm_ms_warm += profiling.replay_us(key, dev, reps=5, cold=False) * cnt / 1e3
-            n_gemm += cnt
+        with ClockSampler(local) as roof_clocks:   # this leg is a dense stream of GEMMs: its own clocks / power state are reported
+            for key, (cnt, _) in calls.items():
+                gemm_ms += profiling.replay_us(key, dev, reps=8, cold=True, batches=3) * cnt / 1e3   # median of 3 batches per shape
+                gemm_ms_warm += profiling.replay_us(key, dev, reps=5, cold=False) * cnt / 1e3
+                n_gemm += cnt
         torch.cuda.empty_cache()
         peak_tf, peak_hbm, how = peaks()
         from t2v_b200 import ops as _ops
@@ -447,7 +451,8 @@ def main():
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": gemm_traffic(),
                 "launches": n_gemm, "distinct_shapes": len(calls), "kernel_ms_per_step": gemm_ms, "share_of_step": None,
                 "algorithmic_tflop_per_step": flops, "peak_source": how,
-                "timing": "per-shape CUDA-graph replay over rotating operand copies (L2-cold), CUDA events",
+                "timing": "per-shape CUDA-graph replay over rotating operand copies (L2-cold), CUDA events, median of 3 batches of >= 24 launches",
+                "clocks": roof_clocks.summary(),
                 "l2_warm": {"kernel_ms_per_step": gemm_ms_warm, "frac": (flops / (gemm_ms_warm / 1e3) / peak_tf) if gemm_ms_warm else None}}
     step.arena.zero_grads()   # the eager passes above accumulated gradients; the timed steps start from a zero buffer
 
@@ -462,11 +467,15 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
+        if args.profile_timed_region:
+            torch.cuda.cudart().cudaProfilerStart()
         e0.record()
         for _ in range(args.steps):
             loss = step(*devin)
         e1.record()
         barrier()
+        if args.profile_timed_region:
+            torch.cuda.cudart().cudaProfilerStop()
     ms = e0.elapsed_time(e1) / args.steps
     # ---- end-to-end leg: pinned host inputs -> device every step, loss read back every step
     for _ in range(2):

@@ -63,11 +63,13 @@ def _nbytes(t):
     return 0
 
 
-def replay_us(key, dev, reps=10, replays=3, cold=False):
+def replay_us(key, dev, reps=10, replays=3, cold=False, batches=1):
     """Average device time (us) of one launch of the recorded call `key`, measured over a replayed CUDA graph of `reps`
     back-to-back launches.  cold=True: the launches rotate over several independent operand sets whose total footprint
     exceeds the 126 MB L2 (at least 4 sets), so no launch finds its operands cached by an earlier one - the situation of
-    the real step, where 2.8 GB of weights and the activations of ~3,400 other launches pass through L2 between two uses."""
+    the real step, where 2.8 GB of weights and the activations of ~3,400 other launches pass through L2 between two uses.
+    batches > 1: the measurement (an average over replays x reps launches) is repeated and the MEDIAN batch is returned - a
+    sub-millisecond window is otherwise at the mercy of one clock ramp or one interfering process."""
     n, ta, tk = key
     fn = getattr(prims, n)
     a = build(ta, dev)
@@ -89,13 +91,17 @@ def replay_us(key, dev, reps=10, replays=3, cold=False):
             fn(*aa, **kk)
     g.replay()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(replays):
-        g.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    us = 1e3 * e0.elapsed_time(e1) / (replays * reps)
+    samples = []
+    for _ in range(max(1, batches)):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(replays):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        samples.append(1e3 * e0.elapsed_time(e1) / (replays * reps))
+    samples.sort()
+    us = samples[len(samples) // 2]
     del g, a, k, sets
     return us
 

@@ -16,6 +16,7 @@ kind = sys.argv[1]
 N, H, W, Ci, Co, KH, KW = (int(v) for v in sys.argv[2:9])
 reps = int(sys.argv[9]) if len(sys.argv) > 9 else 5
 with_stats = "stats" in sys.argv      # forward only: also produce the per-frame GroupNorm statistics in the epilogue
+with_dbias = "dbias" in sys.argv      # wgrad only: also produce the bias gradient (row sums of dy^T) in the same launch
 pads = ((KH - 1) // 2, (KH - 1) // 2, (KW - 1) // 2, (KW - 1) // 2)
 dev = "cuda"
 x = torch.randn(N, H, W, Ci, device=dev).bfloat16()
@@ -23,6 +24,7 @@ w = (torch.randn(Co, KH, KW, Ci, device=dev) * 0.02).bfloat16()
 bias = torch.randn(Co, device=dev)
 dy = torch.randn(N, H, W, Co, device=dev).bfloat16()
 dw = torch.zeros(Co, KH, KW, Ci, device=dev)
+db = torch.zeros(Co, device=dev)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for i in range(reps + 2):
     if i == 2:
@@ -33,7 +35,7 @@ for i in range(reps + 2):
     elif kind == "dgrad":
         prims.conv_dgrad(dy, w, (H, W), 1, pads)
     else:
-        prims.conv_wgrad(x, dy, dw, 1, pads)
+        prims.conv_wgrad(x, dy, dw, 1, pads, dbias=db if with_dbias else None)
 e1.record()
 torch.cuda.synchronize()
 fl = 2.0 * N * H * W * Co * KH * KW * Ci
