@@ -109,3 +109,48 @@ def test_two_ranks_train_identical_lora_weights(tmp_path):
     a, b = torch.load(os.path.join(out, "master0.pt")), torch.load(os.path.join(out, "master1.pt"))
     # identical LoRA initialisation on both ranks, identical (all-reduced) gradients, identical update
     assert torch.equal(a, b)
+
+
+def test_fusions_are_wired_for_every_layer():
+    """Host wiring of the two producer-side fusions, counted on a CPU run over the emulated primitives:
+      * every GroupNorm forward of the UNet is handed the (sum, sum of squares) its producing GEMM accumulated - none computes
+        its own statistics pass;
+      * every biased conv / linear gets its bias gradient out of the weight-gradient launch (dbias argument); the column-sum
+        primitive is left with the per-clip time-embedding gradients (rowbias layers) and the two channel-padded boundary convs."""
+    from t2v_b200 import prims
+    from t2v_b200 import step as S
+    m = _model(train=False)
+    lat, noise, t, text = _inputs(B=1, F=2)
+    counts = {"gn": 0, "gn_with_stats": 0, "wgrad": 0, "wgrad_dbias": 0, "colsum": 0}
+    with emulated_prims():
+        gn0, wg0, cs0 = prims.groupnorm_fwd, prims.conv_wgrad, prims.colsum
+
+        def gn(x, gamma, beta, G, eps, silu, stats=None, fps=1):
+            counts["gn"] += 1
+            counts["gn_with_stats"] += bool(stats)
+            return gn0(x, gamma, beta, G, eps, silu, stats, fps)
+
+        def wg(x, dy, dw, stride=1, pads=(0, 0, 0, 0), dbias=None):
+            counts["wgrad"] += 1
+            counts["wgrad_dbias"] += dbias is not None
+            return wg0(x, dy, dw, stride, pads, dbias)
+
+        def cs(x, out, Sn, P, C):
+            counts["colsum"] += 1
+            return cs0(x, out, Sn, P, C)
+
+        prims.groupnorm_fwd, prims.conv_wgrad, prims.colsum = gn, wg, cs
+        try:
+            loss = S.finetune_loss(m, lat, noise, t, text, S.ddpm_alphas_cumprod())
+            loss.backward()
+        finally:
+            prims.groupnorm_fwd, prims.conv_wgrad, prims.colsum = gn0, wg0, cs0
+    biased = sum(1 for n, p in m.named_parameters() if n.endswith(".bias") and p.dim() == 1 and
+                 n[:-5] + ".weight" in dict(m.named_parameters()) and dict(m.named_parameters())[n[:-5] + ".weight"].dim() >= 2)
+    assert counts["gn"] > 50 and counts["gn_with_stats"] == counts["gn"], counts
+    # rowbias layers: conv1 of every ResnetBlock2D (its bias gradient is the sum of the per-clip time-embedding gradient rows)
+    n_resnets = sum(1 for mod in m.modules() if type(mod).__name__ == "ResnetBlock2D")
+    # + conv_in / conv_out: their 4 latent channels are zero-padded to 8, the padded weight gradient goes through a temporary
+    assert counts["colsum"] == n_resnets + 2, (counts, n_resnets)
+    assert counts["wgrad_dbias"] >= biased - n_resnets - 4 and counts["wgrad_dbias"] > 0.5 * counts["wgrad"], (counts, biased, n_resnets)
+    assert all(p.grad is not None for n, p in m.named_parameters() if n.endswith(".bias")), "a bias lost its gradient"
