@@ -620,6 +620,8 @@ static int conv_wgrad_impl(const void* x, const void* dy, float* dw, float* dbia
                 if (forced_bn && bn != forced_bn) continue;
                 if (bn > 16 && bn - 16 >= Cin) continue;
                 const int stage_bytes = mh * kBlockM * 128 + ((bn + 63) / 64) * 8192;
+                // (the 2 KB tile of ones of the fused bias gradient is budgeted for every candidate, so that the choice with and
+                // without dbias differs only by the UMMA N limit)
                 const int budget = 232448 - 1024 - 256 - kEpilogueStagingBytes - kOnesTileBytes;
                 if (budget / stage_bytes < 3) continue;
                 const int64_t base = int64_t(mt) * ((Cin + bn - 1) / bn) * taps;
