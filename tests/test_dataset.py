@@ -121,3 +121,15 @@ def test_device_resize_normalise_matches_torch_bilinear():
         want = ops_ref.frames_u8_to_nhwc8(fr, hw).float()
         assert got.shape == want.shape and (got[..., 3:] == 0).all()
         assert (got - want).abs().max().item() < 2e-2     # bf16 rounding of values in [-1, 1]
+
+
+def test_sensible_buckets_match_the_reference():
+    """Aspect-ratio bucketing vs vectors produced by the reference's own utils/bucketing.py (tests/golden/make_golden_buckets.py)."""
+    import json
+    from t2v_b200.utils.dataset import sensible_buckets
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "buckets.json")) as f:
+        g = json.load(f)
+    assert len(g["cases"]) >= 90
+    for mw, mh, w, h, ow, oh in g["cases"]:
+        got = sensible_buckets(mw, mh, w, h)
+        assert (int(got[0]), int(got[1])) == (ow, oh), ((mw, mh, w, h), got, (ow, oh))
